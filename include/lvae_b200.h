@@ -1,0 +1,145 @@
+/*
+ * lvae_b200 — C ABI of the B200-native GP-prior ELBO path of L-VAE (SidRama/Longitudinal-VAE).
+ *
+ * The reference is pure Python/PyTorch and has no FFI layer of its own; the drop-in boundary is its Python call
+ * signatures.  Each entry point below names the reference lines whose arithmetic it replaces; the
+ * Python host side (longitudinal-vae_b200/*.py) mirrors the reference's functions over these calls through ctypes.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Unless marked HOST, every pointer is a device pointer
+ * to FP64 data owned by the caller for the duration of the call.  All work is enqueued on `stream` (a cudaStream_t
+ * passed as void*); no call synchronises the device.  Return value: 0 = enqueued, <0 = -(cudaError_t), >0 = invalid
+ * argument (LVAE_E_*).  Cholesky failures (non-PD block) are reported asynchronously in `info` (device int32[4]:
+ * info[0] = 1 + index of the first failing latent for Kzz, info[1] for H, info[2] = 1 + flat (latent*P_b + subject)
+ * for a per-subject block B_p, info[3] for the natural-gradient update); the Python wrapper raises RuntimeError like
+ * torch.cholesky does.
+ */
+#ifndef LVAE_B200_H
+#define LVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVAE_MAX_COMPONENTS 16
+#define LVAE_MAX_MASKS 3
+#define LVAE_MAX_M 256
+#define LVAE_MAX_T 40
+#define LVAE_SPEC_STRIDE 10
+
+/* factor types inside a component */
+#define LVAE_CAT 0 /* 1[x1 == x2]      kernel_spec.py:31-32, GP_model.py:43-53 */
+#define LVAE_BIN 1 /* 1[x1 + x2 == 2]  kernel_spec.py:22-23, GP_model.py:31-41 */
+
+#define LVAE_E_BADARG 1
+#define LVAE_E_TOO_LARGE 2
+#define LVAE_E_SPEC 3
+
+/*
+ * Additive-kernel structure (kernel_gen.py:199-310 / GP_model.py:146-236), flattened.
+ * HOST int32 table, one row of LVAE_SPEC_STRIDE ints per component, K0 components first, then K1:
+ *   [0] rbf_dim   covariate column of the squared-exponential factor, or -1 if the component has none
+ *   [1] ls_index  row of `lengthscale` used by that factor (ignored if rbf_dim < 0)
+ *   [2] n_masks   number of categorical/binary factors (0..3)
+ *   [3+2i] type (LVAE_CAT | LVAE_BIN), [4+2i] covariate column, i < n_masks
+ * component value:  outputscale[c][l] * prod(masks) * exp(-(x1[rbf_dim]-x2[rbf_dim])^2 / (2 lengthscale[ls][l]^2))
+ */
+typedef struct {
+    int32_t n_comp0;     /* components without the id covariate (K0) */
+    int32_t n_comp1;     /* components with the id covariate (K1)    */
+    int32_t n_ls;        /* rows of `lengthscale`                    */
+    const int32_t* spec; /* HOST [(n_comp0+n_comp1) * LVAE_SPEC_STRIDE] */
+} lvae_kernel_spec_t;
+
+/* Dense additive kernel  out[l, i, j] = sum_c k_c(x1[i], x2[j]) (+ diag_add[l] on i == j)   — replaces
+ * `covar_module(x1, x2).evaluate()` (elbo_functions.py:171-172; gpytorch Kernel.__call__) and GP_model.AdditiveKernel.
+ * x1: [n1,Q] shared by all latents (x1_latent_stride = 0) or [n_batch,n1,Q] (stride n1*Q); same for x2.
+ * n_batch matrices are produced (n_batch a multiple of L); matrix b uses the hyper-parameters of latent b % L, which
+ * covers the reference's [P_b,L,T,Q] stacking (elbo_functions.py:168-174) with n_batch = P_b*L.
+ * comp_begin/comp_end select K0 (0..n_comp0) or K1 (n_comp0..n_comp0+n_comp1). */
+int lvae_kernel_dense_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int32_t comp_end, int32_t L,
+                          int32_t n_batch, int32_t Q, const double* x1, int64_t x1_latent_stride, int32_t n1, const double* x2,
+                          int64_t x2_latent_stride, int32_t n2, const double* lengthscale, const double* outputscale,
+                          const double* diag_add, double* out, void* stream);
+
+/* Per-subject blocks  out[l, off2[p] + t*T_p + t'] = K(x_p[t], x_p[t'])  — replaces the [L,P_b,T,T] stacks of
+ * elbo_functions.py:173-174 and the per-subject evaluations of 269-271.  offsets: device int32 [P_b+1] row offsets;
+ * off2[p] = sum_{q<p} T_q^2 is computed on the device; block_stride = sum_p T_p^2 (elements per latent). */
+int lvae_kernel_blocks_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int32_t comp_end, int32_t L, int32_t Q,
+                           const double* x, const int32_t* offsets, int32_t P_b, int64_t block_stride,
+                           const double* lengthscale, const double* outputscale, const double* diag_add, double* out,
+                           void* stream);
+
+/* Batched Cholesky, in place, lower, n <= 256: replaces torch.cholesky (elbo_functions.py:177,179,185).
+ * info: device int32[1], set to 1 + index of the first non-PD matrix (never cleared). */
+int lvae_potrf_batched_f64(double* A, int32_t n, int64_t batch_stride, int32_t batch, int32_t* info, void* stream);
+/* Explicit inverse from the Cholesky factor: replaces cholesky_solve(I, L) (elbo_functions.py:178,180,186). */
+int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n, int64_t batch_stride, int32_t batch,
+                           void* stream);
+
+/* One minibatch of the Hensman-style KL upper bound and ALL its gradients (elbo_functions.py:144-216 / 219-307 plus the
+ * reverse pass autograd would run, SURVEY 8a adjoints). */
+typedef struct {
+    /* sizes */
+    int32_t L, M, Q, P_b, N_b, T_max; /* P_b, N_b: subjects / rows held by THIS GPU; T_max = max rows per subject */
+    int64_t sum_T2;                   /* sum_p T_p^2 over this GPU's subjects */
+    int32_t natural_gradient; /* 1: emit grad_m/grad_H (elbo_functions.py:208-214); 0: emit d_m/d_H (autograd) */
+    int32_t path;             /* 0 = auto, 1 = generic kernels, 2 = fused DMMA kernel (M <= 64 only) */
+    double scale;             /* P_tot / P_b                                           (elbo_functions.py:204) */
+    double const_term;        /* L*P_tot*T/2 (204) or L*N/2 (299), subtracted once     */
+    double eps;               /* jitter on Kzz only (176)                               */
+    lvae_kernel_spec_t ks;
+    /* inputs */
+    const double* x;           /* [N_b,Q]  rows grouped by subject, subject p = rows offsets[p]..offsets[p+1]-1 */
+    const int32_t* offsets;    /* device int32 [P_b+1] */
+    const double* mu;          /* [N_b,L] */
+    const double* log_v;       /* [N_b,L] */
+    const double* z;           /* [L,M,Q] */
+    const double* m;           /* [L,M]   */
+    const double* H;           /* [L,M,M] SPD */
+    const double* lengthscale; /* [n_ls,L] */
+    const double* outputscale; /* [n_comp0+n_comp1,L] */
+    const double* noise;       /* [L] */
+    /* outputs */
+    double* kld_per_latent; /* [L]; kld_total = sum                                   */
+    double* grad_m;         /* [L,M]   natural-gradient "gradients" (NOT scaled by P_tot/P_b, 208-214) or d kld/d m */
+    double* grad_H;         /* [L,M,M]                                                                or d kld/d H */
+    double* d_mu;           /* [N_b,L] d kld_total / d mu     */
+    double* d_log_v;        /* [N_b,L] d kld_total / d log_v  */
+    double* d_lengthscale;  /* [n_ls,L]   */
+    double* d_outputscale;  /* [n_comp,L] */
+    double* d_noise;        /* [L]        */
+    /* scratch, sized by lvae_kld_workspace_doubles(); stats are the SVGP sufficient statistics that are summed across
+     * GPUs between lvae_kld_subjects_f64 and lvae_kld_tail_f64 */
+    double* stats;     /* [L, lvae_kld_stats_stride()] */
+    double* workspace; /* lvae_kld_workspace_doubles() doubles */
+    int32_t* info;     /* device int32[4] */
+} lvae_kld_problem_t;
+
+int64_t lvae_kld_stats_stride(int32_t M, int32_t n_ls, int32_t n_comp);
+int64_t lvae_kld_workspace_doubles(const lvae_kld_problem_t* p);
+
+/* Per-latent M x M work that does not depend on the minibatch rows: Kzz, chol, Kzz^-1, chol H, H^-1, a = Kzz^-1 m,
+ * G = Kzz^-1 H Kzz^-1 (elbo_functions.py:172,176-178,185-186,194). */
+int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream);
+/* Per-subject work, sharded by subject across GPUs: kernel blocks, chol/inverse of B_p, S, A..F partial sums, ng1,
+ * d_mu, d_log_v and the subject part of the hyper-parameter gradients (173-174,179-184,189-196, 264-288). */
+int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream);
+/* Per-latent tail on the (all-reduced) statistics: D, E, KL[q(u)||p(u)], kld, grad_m, grad_H, Kzz adjoint (193-214). */
+int lvae_kld_tail_f64(const lvae_kld_problem_t* p, void* stream);
+/* head + subjects + tail on one GPU */
+int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream);
+
+/* Natural-gradient update of (m, H), in place (training.py:129-135).  workspace: 4*L*M*M doubles; info[3]. */
+int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, double lr, int32_t L, int32_t M,
+                     double* workspace, int32_t* info, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t lvae_launch_count(void);
+const char* lvae_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVAE_B200_H */

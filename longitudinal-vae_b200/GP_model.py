@@ -1,0 +1,161 @@
+"""Drop-in for the reference's GP_model.py (its gpytorch-free kernel/likelihood restatement, GP_model.py:7-236).
+
+Same class names, constructor arguments, parameter names (`_log_noise`, `_log_lengthscale`, `_log_scale`) and buffers
+(`min_log_*`); values are `exp(min_log + softplus(raw - min_log))` with `min_log = -16` and float32 initialisation as in
+the reference (GP_model.py:16-18,65-67,97-99).  `forward(x1, x2)` returns a dense tensor computed by the CUDA
+dense-kernel op; latent dimension first (`[L, n1, n2]`), as the reference's classes broadcast.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import ops
+from .spec import FlatComponent, build_structure, flatten, latent_count
+
+
+def _bounded(raw, min_log):
+    return torch.exp(min_log + F.softplus(raw - min_log))
+
+
+class Likelihoods(nn.Module):
+    def __init__(self, latent_dim, noise, constrain=True):
+        super().__init__()
+        self.latent_dim = latent_dim
+        min_log_noise = torch.Tensor([-16.0])
+        init = torch.log(torch.as_tensor(noise, dtype=torch.float32) - torch.exp(min_log_noise))
+        self._log_noise = nn.Parameter(torch.Tensor([init] * latent_dim), requires_grad=constrain)
+        self.register_buffer('min_log_noise', min_log_noise * torch.ones(1))
+
+    @property
+    def noise(self):
+        return _bounded(self._log_noise, self.min_log_noise)
+
+    @noise.setter
+    def noise(self, noise):
+        with torch.no_grad():
+            self._log_noise.copy_(torch.log(torch.as_tensor(noise) - torch.exp(self.min_log_noise)))
+
+
+class _DenseModule(nn.Module):
+    def forward(self, x1, x2):
+        comps = flatten(self)
+        L = latent_count(comps, default=1)
+        structure, ls, os_ = build_structure(comps, [], L, device=x1.device)
+        a = x1 if x1.dim() < 3 or x1.shape[0] == L else x1.expand(L, *x1.shape[-2:])
+        b = x2 if x2.dim() < 3 or x2.shape[0] == L else x2.expand(L, *x2.shape[-2:])
+        return ops.kernel_dense(structure, ls, os_, a, b, "all")
+
+
+class BinKernel(_DenseModule):
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def _flat_components(self):
+        return [FlatComponent(None, [('bin', self.dim, None)])]
+
+
+class CatKernel(_DenseModule):
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def _flat_components(self):
+        return [FlatComponent(None, [('cat', self.dim, None)])]
+
+
+class RbfKernel(_DenseModule):
+    def __init__(self, dim, latent_dim=1, lengthscale=2.5):
+        super().__init__()
+        self.dim = dim
+        self.latent_dim = latent_dim
+        min_log = torch.Tensor([-16.0])
+        init = torch.log(torch.as_tensor(lengthscale, dtype=torch.float32) - torch.exp(min_log))
+        self._log_lengthscale = nn.Parameter(torch.Tensor([init] * latent_dim), requires_grad=True)
+        self.register_buffer('min_log_lengthscale', min_log * torch.ones(1))
+
+    @property
+    def lengthscale(self):
+        return _bounded(self._log_lengthscale, self.min_log_lengthscale)
+
+    @lengthscale.setter
+    def lengthscale(self, lengthscale):
+        with torch.no_grad():
+            self._log_lengthscale.copy_(torch.log(torch.as_tensor(lengthscale) - torch.exp(self.min_log_lengthscale)))
+
+    def _flat_components(self):
+        return [FlatComponent(None, [('rbf', self.dim, self.lengthscale.reshape(-1))])]
+
+
+class ScaleKernel(_DenseModule):
+    def __init__(self, kernel, latent_dim=1, scale=math.log(2)):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.kernel = kernel
+        min_log = torch.Tensor([-16.0])
+        init = torch.log(torch.as_tensor(scale, dtype=torch.float32) - torch.exp(min_log))
+        self._log_scale = nn.Parameter(torch.Tensor([init] * latent_dim), requires_grad=True)
+        self.register_buffer('min_log_scale', min_log * torch.ones(1))
+
+    @property
+    def scale(self):
+        return _bounded(self._log_scale, self.min_log_scale)
+
+    @scale.setter
+    def scale(self, scale):
+        with torch.no_grad():
+            self._log_scale.copy_(torch.log(torch.as_tensor(scale) - torch.exp(self.min_log_scale)))
+
+    def _flat_components(self):
+        s = FlatComponent(self.scale.reshape(-1), [])
+        return [s.times(c) for c in flatten(self.kernel)]
+
+
+class AdditiveKernel(_DenseModule):
+    def __init__(self, kernels):
+        super().__init__()
+        self.kernels = nn.ModuleList(kernels)
+
+    def _flat_components(self):
+        return [c for k in self.kernels for c in flatten(k)]
+
+
+class ProductKernel(_DenseModule):
+    def __init__(self, kernel1, kernel2):
+        super().__init__()
+        self.k1 = kernel1
+        self.k2 = kernel2
+
+    def _flat_components(self):
+        return [a.times(b) for a in flatten(self.k1) for b in flatten(self.k2)]
+
+
+def generate_kernel_batched(latent_dim, cat_kernel, bin_kernel, sqexp_kernel, cat_int_kernel, bin_int_kernel,
+                            covariate_missing_val, id_covariate):
+    """(K0, K1) AdditiveKernels; same K0/K1 assignment and component order as kernel_gen (GP_model.py:146-236)."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    missing = [d['covariate'] for d in covariate_missing_val]
+
+    def masked(kernel, covariate):
+        if covariate in missing:
+            return ProductKernel(kernel, BinKernel(covariate_missing_val[missing.index(covariate)]['mask']))
+        return kernel
+
+    k0, k1 = [], []
+    for d in cat_kernel:
+        (k1 if d == id_covariate else k0).append(ScaleKernel(masked(CatKernel(d), d), latent_dim))
+    for d in sqexp_kernel:
+        k0.append(ScaleKernel(masked(RbfKernel(d, latent_dim), d), latent_dim))
+    for d in bin_kernel:
+        k0.append(ScaleKernel(masked(BinKernel(d), d), latent_dim))
+    for e in cat_int_kernel:
+        prod = ProductKernel(masked(CatKernel(e['cat_covariate']), e['cat_covariate']),
+                             masked(RbfKernel(e['cont_covariate'], latent_dim), e['cont_covariate']))
+        (k1 if e['cat_covariate'] == id_covariate else k0).append(ScaleKernel(prod, latent_dim))
+    for e in bin_int_kernel:
+        prod = ProductKernel(masked(BinKernel(e['bin_covariate']), e['bin_covariate']),
+                             masked(RbfKernel(e['cont_covariate'], latent_dim), e['cont_covariate']))
+        k0.append(ScaleKernel(prod, latent_dim))
+    return AdditiveKernel(k0).to(device), AdditiveKernel(k1).to(device)

@@ -1,0 +1,203 @@
+// Materialising kernels: dense additive kernel matrices and per-subject blocks from covariates, batched
+// Cholesky / explicit inverse.  These back the drop-in `covar_module(x1, x2).evaluate()` of the host mirror and the
+// parity tests on kernel matrices and Cholesky factors; the training hot path never materialises Kxz (see
+// lvae_subjects_fused.cu).  The dense kernel is HBM-write-bound: 8*L*n1*n2 bytes out, covariates stay in L1/L2.
+#include "lvae_host.h"
+#include "lvae_linalg.cuh"
+
+int64_t& lvae_launch_counter() {
+    static int64_t c = 0;
+    return c;
+}
+
+int lvae_make_devspec(const lvae_kernel_spec_t* ks, int Q, DevSpec* out) {
+    if (!ks || !ks->spec) return LVAE_E_BADARG;
+    const int nc = ks->n_comp0 + ks->n_comp1;
+    if (nc < 0 || nc > LVAE_MAXC || ks->n_ls < 0 || ks->n_ls > LVAE_MAXC) return LVAE_E_SPEC;
+    DevSpec s;
+    memset(&s, 0, sizeof(s));
+    s.n0 = ks->n_comp0;
+    s.n1 = ks->n_comp1;
+    s.n_ls = ks->n_ls;
+    for (int c = 0; c < nc; ++c) {
+        const int32_t* r = ks->spec + (size_t)c * LVAE_SPEC_STRIDE;
+        if (r[0] >= Q || r[0] < -1) return LVAE_E_SPEC;
+        if (r[0] >= 0 && (r[1] < 0 || r[1] >= ks->n_ls)) return LVAE_E_SPEC;
+        if (r[2] < 0 || r[2] > LVAE_MAX_MASKS) return LVAE_E_SPEC;
+        s.rbf_dim[c] = (signed char)r[0];
+        s.ls_idx[c] = (signed char)(r[0] >= 0 ? r[1] : 0);
+        s.n_mask[c] = (signed char)r[2];
+        for (int i = 0; i < r[2]; ++i) {
+            const int ty = r[3 + 2 * i], dm = r[4 + 2 * i];
+            if ((ty != LVAE_CAT && ty != LVAE_BIN) || dm < 0 || dm >= Q) return LVAE_E_SPEC;
+            s.mask_type[c][i] = (signed char)ty;
+            s.mask_dim[c][i] = (signed char)dm;
+        }
+    }
+    *out = s;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dense kernel: grid (ceil(n2/64), ceil(n1/4), L), block (64, 4); each thread one output element, coalesced on j.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dense(DevSpec sp, int c0, int c1, int Q, const double* __restrict__ x1,
+                                               int64_t s1, int n1, const double* __restrict__ x2, int64_t s2, int n2,
+                                               const double* __restrict__ ls, const double* __restrict__ os, int L,
+                                               const double* __restrict__ diag_add, double* __restrict__ out) {
+    __shared__ double hil2[LVAE_MAXC], osc[LVAE_MAXC];
+    const int b = blockIdx.z, l = b % L;
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; hil2[t] = 0.5 / (v * v); }
+    if (t < sp.n0 + sp.n1) osc[t] = os[(size_t)t * L + l];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= n1 || j >= n2) return;
+    const double* xa = x1 + (size_t)b * s1 + (size_t)i * Q;
+    const double* xb = x2 + (size_t)b * s2 + (size_t)j * Q;
+    double acc = 0.0, d2;
+    for (int c = c0; c < c1; ++c) acc += osc[c] * comp_value(sp, c, xa, xb, hil2, d2);
+    if (diag_add && i == j) acc += diag_add[l];
+    out[((size_t)b * n1 + i) * n2 + j] = acc;
+}
+
+extern "C" int lvae_kernel_dense_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int32_t comp_end, int32_t L,
+                                     int32_t n_batch, int32_t Q, const double* x1, int64_t s1, int32_t n1, const double* x2, int64_t s2,
+                                     int32_t n2, const double* lengthscale, const double* outputscale,
+                                     const double* diag_add, double* out, void* stream) {
+    DevSpec sp;
+    int rc = lvae_make_devspec(ks, Q, &sp);
+    if (rc) return rc;
+    if (comp_begin < 0 || comp_end > sp.n0 + sp.n1 || comp_begin > comp_end || L <= 0) return LVAE_E_BADARG;
+    if (n_batch <= 0 || n_batch % L != 0) return LVAE_E_BADARG;
+    if (n_batch > 65535) return LVAE_E_TOO_LARGE;
+    if (n1 == 0 || n2 == 0) return 0;
+    dim3 block(64, 4), grid((n2 + 63) / 64, (n1 + 3) / 4, n_batch);
+    if (grid.y > 65535) return LVAE_E_TOO_LARGE;
+    k_dense<<<grid, block, 0, (cudaStream_t)stream>>>(sp, comp_begin, comp_end, Q, x1, s1, n1, x2, s2, n2, lengthscale,
+                                                      outputscale, L, diag_add, out);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-subject blocks: grid (P_b, L); CTA loops over the T_p x T_p block.  off2[p] computed by a prefix over T_q^2
+// (serial per CTA over p' < p would be O(P^2); instead thread 0 of each CTA reads a precomputed table).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_block_offsets(const int32_t* __restrict__ offsets, int P_b, int64_t* __restrict__ off2) {
+    // single CTA exclusive scan of T_p^2 (P_b up to ~1e6: chunked serial per thread + block scan)
+    extern __shared__ int64_t part[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (P_b + nt - 1) / nt;
+    const int b = tid * per, e = min(P_b, b + per);
+    int64_t s = 0;
+    for (int p = b; p < e; ++p) { const int64_t T = offsets[p + 1] - offsets[p]; s += T * T; }
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < nt; ++i) { const int64_t v = part[i]; part[i] = run; run += v; }
+        off2[P_b] = run;
+    }
+    __syncthreads();
+    s = part[tid];
+    for (int p = b; p < e; ++p) { off2[p] = s; const int64_t T = offsets[p + 1] - offsets[p]; s += T * T; }
+}
+
+__global__ void __launch_bounds__(128) k_blocks(DevSpec sp, int c0, int c1, int Q, const double* __restrict__ x,
+                                                const int32_t* __restrict__ offsets, const int64_t* __restrict__ off2,
+                                                int64_t block_stride, const double* __restrict__ ls,
+                                                const double* __restrict__ os, int L,
+                                                const double* __restrict__ diag_add, double* __restrict__ out) {
+    __shared__ double hil2[LVAE_MAXC], osc[LVAE_MAXC];
+    const int p = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
+    if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; hil2[t] = 0.5 / (v * v); }
+    if (t < sp.n0 + sp.n1) osc[t] = os[(size_t)t * L + l];
+    __syncthreads();
+    const int r0 = offsets[p], T = offsets[p + 1] - r0;
+    double* o = out + (size_t)l * block_stride + off2[p];
+    for (int e = t; e < T * T; e += blockDim.x) {
+        const int i = e / T, j = e % T;
+        const double* xa = x + (size_t)(r0 + i) * Q;
+        const double* xb = x + (size_t)(r0 + j) * Q;
+        double acc = 0.0, d2;
+        for (int c = c0; c < c1; ++c) acc += osc[c] * comp_value(sp, c, xa, xb, hil2, d2);
+        if (diag_add && i == j) acc += diag_add[l];
+        o[e] = acc;
+    }
+}
+
+int lvae_block_offsets(const int32_t* offsets, int P_b, int64_t* off2, cudaStream_t st) {
+    // simple and robust: one thread per subject is not a scan; do the scan in one CTA of 256 threads
+    k_block_offsets<<<1, 256, 256 * sizeof(int64_t), st>>>(offsets, P_b, off2);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+extern "C" int lvae_kernel_blocks_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int32_t comp_end, int32_t L,
+                                      int32_t Q, const double* x, const int32_t* offsets, int32_t P_b,
+                                      int64_t block_stride, const double* lengthscale, const double* outputscale,
+                                      const double* diag_add, double* out, void* stream) {
+    DevSpec sp;
+    int rc = lvae_make_devspec(ks, Q, &sp);
+    if (rc) return rc;
+    if (comp_begin < 0 || comp_end > sp.n0 + sp.n1 || comp_begin > comp_end || L <= 0 || L > 65535) return LVAE_E_BADARG;
+    if (P_b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t* off2 = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&off2, sizeof(int64_t) * ((size_t)P_b + 1), st);
+    if (e != cudaSuccess) return lvae_cuda_rc(e);
+    rc = lvae_block_offsets(offsets, P_b, off2, st);
+    if (!rc) {
+        k_blocks<<<dim3(P_b, L), 128, 0, st>>>(sp, comp_begin, comp_end, Q, x, offsets, off2, block_stride, lengthscale,
+                                               outputscale, L, diag_add, out);
+        LVAE_COUNT_LAUNCH();
+        rc = lvae_cuda_rc(cudaGetLastError());
+    }
+    cudaFreeAsync(off2, st);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batched Cholesky / inverse (generic, one CTA per matrix, operating in place in global/L2 memory)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_potrf(double* __restrict__ A, int n, int64_t stride, int32_t* info) {
+    __shared__ int flag;
+    const int rc = cta_cholesky(A + (size_t)blockIdx.x * stride, n, n, &flag);
+    if (rc && threadIdx.x == 0) atomicCAS(info, 0, (int)blockIdx.x + 1);
+}
+
+__global__ void __launch_bounds__(256) k_potri(const double* __restrict__ Lc, double* __restrict__ Ainv,
+                                               double* __restrict__ tmp, int n, int64_t stride) {
+    const double* Lb = Lc + (size_t)blockIdx.x * stride;
+    double* X = tmp + (size_t)blockIdx.x * n * n;
+    cta_tri_inverse(Lb, X, n, n);
+    cta_gram_lower(X, Ainv + (size_t)blockIdx.x * stride, n, n);
+}
+
+extern "C" int lvae_potrf_batched_f64(double* A, int32_t n, int64_t batch_stride, int32_t batch, int32_t* info,
+                                      void* stream) {
+    if (n <= 0 || n > LVAE_MAX_M || batch < 0 || batch_stride < (int64_t)n * n) return LVAE_E_BADARG;
+    if (batch == 0) return 0;
+    k_potrf<<<batch, 256, 0, (cudaStream_t)stream>>>(A, n, batch_stride, info);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+extern "C" int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n, int64_t batch_stride, int32_t batch,
+                                      void* stream) {
+    if (n <= 0 || n > LVAE_MAX_M || batch < 0 || batch_stride < (int64_t)n * n) return LVAE_E_BADARG;
+    if (batch == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* tmp = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&tmp, sizeof(double) * (size_t)batch * n * n, st);
+    if (e != cudaSuccess) return lvae_cuda_rc(e);
+    k_potri<<<batch, 256, 0, st>>>(Lc, Ainv, tmp, n, batch_stride);
+    LVAE_COUNT_LAUNCH();
+    int rc = lvae_cuda_rc(cudaGetLastError());
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+extern "C" int64_t lvae_launch_count(void) { return lvae_launch_counter(); }
+extern "C" const char* lvae_version(void) { return "lvae_b200 0.1 (sm_100a, fp64)"; }

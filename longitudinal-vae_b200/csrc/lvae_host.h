@@ -1,0 +1,10 @@
+// Host-side helpers shared by the translation units of liblvae_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "lvae_common.cuh"
+
+static inline int lvae_cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
+int lvae_make_devspec(const lvae_kernel_spec_t* ks, int Q, DevSpec* out);
+int lvae_block_offsets(const int32_t* offsets, int P_b, int64_t* off2, cudaStream_t st);

@@ -1,0 +1,22 @@
+// Internal: workspace layout shared by the KLD kernels (offsets in doubles into lvae_kld_problem_t::workspace).
+#pragma once
+#include "lvae_host.h"
+
+struct KldLayout {
+    int64_t Ki, Hi, G, W, T1, T2, T3;   // [L, M*M] each
+    int64_t a;                          // [L, M]
+    int64_t logdet;                     // [L, 2]  (log det Kzz, log det H)
+    int64_t Bi;                         // [L, sum_T2]  explicit inverses of the per-subject blocks
+    int64_t Bi_stride;                  // = sum_T2
+    int64_t off2;                       // int64 [P_b+1] prefix of T_p^2
+    int64_t part;                       // [nchunk, L, stride] per-CTA partial statistics of the subject pass
+    int64_t ppart;                      // [nchunk, L, NSCAL+nh] per-CTA partials of the prep pass
+    int64_t total;
+    int64_t stride;                     // statistics row length
+    int nh, nchunk;
+};
+
+KldLayout lvae_layout(const lvae_kld_problem_t* p);
+int lvae_chunks(int P_b, int L);
+// fused DMMA subject pass for M <= 64 (lvae_subjects_fused.cu); fills the same `part` partials as the generic kernel
+int lvae_subjects_fused_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);

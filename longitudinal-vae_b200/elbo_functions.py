@@ -1,0 +1,129 @@
+"""Drop-in for the reference's elbo_functions.py on the Hensman minibatch path (elbo_functions.py:144-307).
+
+`minibatch_KLD_upper_bound` and `minibatch_KLD_upper_bound_iter` keep the reference's call signatures and return
+`(kld_total, grad_m, grad_H)`.  The arithmetic runs in liblvae_b200.so: one head kernel (per-latent M x M work), the
+per-subject pass (kernel blocks built from covariates, batched Cholesky/inverse of the T x T blocks, S and the A..F partial
+sums, fused with the reverse pass), an optional NCCL all-reduce of the sufficient statistics when the subjects are
+sharded across GPUs, and one tail kernel.  `kld_total` is an autograd node w.r.t. mu, log_v, every kernel
+hyper-parameter, the likelihood noise and (natural_gradient=False) m and H; its gradients are produced by the same
+launches (closed-form adjoints) and scaled by the incoming gradient in backward.
+"""
+import torch
+
+from . import ops
+from .spec import build_structure, flatten
+
+_GROUP = None        # torch.distributed process group over which the minibatch subjects are sharded (None = 1 GPU)
+_PATH = 0            # 0 auto, 1 generic kernels, 2 fused DMMA kernel
+
+
+def set_process_group(group):
+    """Shard mode: every rank passes ITS rows; P_batch / P_in_current_batch stay GLOBAL minibatch subject counts."""
+    global _GROUP
+    _GROUP = group
+
+
+def set_kernel_path(path):
+    global _PATH
+    _PATH = int(path)
+
+
+def _noise_of(likelihood, L, dtype, device):
+    src = getattr(likelihood, "noise_covar", likelihood)
+    return src.noise.reshape(-1).to(dtype=dtype, device=device).expand(L)
+
+
+class _KldBound(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, log_v, m, H, lengthscale, outputscale, noise, meta):
+        st = meta["structure"]
+        x, z, offsets = meta["x"], meta["z"], meta["offsets"]
+        L, M, Q = meta["L"], H.shape[-1], x.shape[1]
+        call = ops.KldCall(st, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"], meta["sum_T2"], x.device,
+                           natural_gradient=meta["natural_gradient"], path=_PATH)
+        call.bind(x, offsets, mu, log_v, z, m.reshape(L, M), H, lengthscale, outputscale, noise, meta["scale"],
+                  meta["const_term"], meta["eps"])
+        call.head()
+        call.subjects()
+        if _GROUP is not None:
+            torch.distributed.all_reduce(call.stats, group=_GROUP)      # SVGP sufficient statistics over NVLink
+        call.tail()
+        if meta.get("check", True):
+            call.raise_on_info()
+        kld = call.kld_per_latent.sum()
+        ctx.call = call
+        ctx.ng = meta["natural_gradient"]
+        ctx.mshape = m.shape
+        ctx.mark_non_differentiable(call.grad_m, call.grad_H)
+        return kld, call.grad_m.view(L, M, 1), call.grad_H
+
+    @staticmethod
+    def backward(ctx, g, _gm, _gH):
+        c = ctx.call
+        d_m = d_H = None
+        if not ctx.ng:
+            d_m, d_H = g * c.grad_m.view(ctx.mshape), g * c.grad_H
+        return (g * c.d_mu, g * c.d_log_v, d_m, d_H, g * c.d_lengthscale, g * c.d_outputscale, g * c.d_noise, None)
+
+
+def _structure_of(covar_module0, covar_module1, L, device):
+    return build_structure(flatten(covar_module0), flatten(covar_module1), L, device=device)
+
+
+def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets, T_max, sum_T2, mu, log_v, z, scale,
+         const_term, natural_gradient, eps):
+    if not x.is_cuda:
+        raise RuntimeError("lvae_b200: the GP-prior ELBO op needs CUDA tensors (no CPU fallback)")
+    L = latent_dim
+    f64 = torch.float64
+    st, ls, os_ = _structure_of(covar_module0, covar_module1, L, x.device)
+    noise = _noise_of(likelihood, L, f64, x.device)
+    if z.dim() == 2:
+        z = z.unsqueeze(0).expand(L, -1, -1)
+    meta = dict(structure=st, x=x.to(f64), z=z.to(f64), offsets=offsets, L=L, T_max=int(T_max), sum_T2=int(sum_T2),
+                scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient))
+    kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), ls, os_, noise, meta)
+    if natural_gradient:
+        return kld, gm, gH
+    return kld, None, None
+
+
+def minibatch_KLD_upper_bound(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z, P_tot,
+                              P_batch, T, natural_gradient, eps):
+    """Unbiased minibatch estimate of the KL upper bound, fixed T rows per subject (elbo_functions.py:144-216).
+
+    train_xt [N_b,Q] is subject-major with exactly T rows per subject (the reference reshapes without checking ids,
+    line 168).  Returns (kld_total, grad_m [L,M,1], grad_H [L,M,M]); the natural-gradient terms are not scaled by
+    P_tot/P_batch, as in the reference (208-214)."""
+    N_b = train_xt.shape[0]
+    P_loc = P_batch if _GROUP is None else N_b // T
+    if P_loc * T != N_b:
+        raise RuntimeError(f"shape '[{P_batch}, {T}, {train_xt.shape[1]}]' is invalid for input of size {train_xt.numel()}")
+    offsets = torch.arange(0, N_b + 1, T, dtype=torch.int32, device=train_xt.device)
+    return _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, offsets, T, P_loc * T * T, mu,
+                log_v, z, P_tot / P_batch, latent_dim * P_tot * T / 2, natural_gradient, eps)
+
+
+def group_by_subject(ids):
+    """Subject grouping of elbo_functions.py:264-267, bit-exact: subjects = sorted unique ids; rows of a subject in their
+    original order.  Returns (row order or None if already grouped, offsets int32 [P+1] on the device, T_max, sum_T2)."""
+    uniq, inverse, counts = torch.unique(ids, sorted=True, return_inverse=True, return_counts=True)
+    order = torch.argsort(inverse, stable=True)
+    counts_h = counts.cpu()                       # one sync; torch.unique(...).tolist() in the reference syncs as well
+    offsets = torch.zeros(counts_h.numel() + 1, dtype=torch.int64)
+    torch.cumsum(counts_h, 0, out=offsets[1:])
+    grouped = bool((order == torch.arange(order.numel(), device=order.device)).all())
+    return (None if grouped else order, offsets.to(torch.int32).to(ids.device), int(counts_h.max()),
+            int((counts_h * counts_h).sum()))
+
+
+def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z, P,
+                                   P_in_current_batch, N, natural_gradient, id_covariate, eps):
+    """Same bound for irregular numbers of rows per subject (elbo_functions.py:219-307): subjects are the sorted unique
+    values of column `id_covariate`; the constant term is L*N/2 with N the number of rows of the whole data set."""
+    order, offsets, T_max, sum_T2 = group_by_subject(train_xt[:, id_covariate])
+    if order is not None:
+        train_xt, mu, log_v = train_xt[order], mu[order], log_v[order]
+    kld, gm, gH = _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, offsets, T_max, sum_T2, mu,
+                       log_v, z, P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps)
+    return kld.reshape(1), gm, gH

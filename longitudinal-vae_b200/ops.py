@@ -1,0 +1,168 @@
+"""Thin Python wrappers over the C ABI (include/lvae_b200.h): tensor allocation, pointer passing, error mapping."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KldProblemT, check, make_spec, ptr, require_cuda, stream_ptr
+
+F64 = torch.float64
+
+
+def _c(t):
+    return t.detach().to(F64).contiguous()
+
+
+def kernel_dense(structure, lengthscale, outputscale, x1, x2, which="all", diag_add=None):
+    """Dense additive kernel [B, n1, n2] on the GPU.  x: [n,Q] (shared) or [B,n,Q]; B a multiple of L (matrix b uses the
+    hyper-parameters of latent b % L).  which: "k0" | "k1" | "all".  Replaces covar_module(x1,x2).evaluate()."""
+    lib = require_cuda(x1, x2, lengthscale, outputscale)
+    L = outputscale.shape[1]
+    lo, hi = {"k0": (0, structure.n_comp0), "k1": (structure.n_comp0, structure.n_comp),
+              "all": (0, structure.n_comp)}[which]
+    x1, x2 = _c(x1), _c(x2)
+    B = max(L, x1.shape[0] if x1.dim() == 3 else 1, x2.shape[0] if x2.dim() == 3 else 1)
+    s1 = x1.shape[-2] * x1.shape[-1] if x1.dim() == 3 else 0
+    s2 = x2.shape[-2] * x2.shape[-1] if x2.dim() == 3 else 0
+    for t in (x1, x2):
+        if t.dim() == 3 and t.shape[0] != B:
+            raise RuntimeError("lvae_b200: batched covariates must share the leading dimension")
+    n1, n2, Q = x1.shape[-2], x2.shape[-2], x1.shape[-1]
+    out = torch.empty(B, n1, n2, dtype=F64, device=x1.device)
+    ks, keep = make_spec(structure)
+    ls, os_ = _c(lengthscale), _c(outputscale)
+    da = _c(diag_add) if diag_add is not None else None
+    with torch.cuda.device(x1.device):
+        rc = lib.lvae_kernel_dense_f64(C.byref(ks), lo, hi, L, B, Q, ptr(x1), s1, n1, ptr(x2), s2, n2, ptr(ls),
+                                       ptr(os_), ptr(da), ptr(out), stream_ptr(x1.device))
+    check(rc, "lvae_kernel_dense_f64")
+    return out
+
+
+def kernel_blocks(structure, lengthscale, outputscale, x, offsets_dev, sum_T2, which="k0", diag_add=None):
+    """Per-subject blocks, flat [L, sum_T2] (block p of latent l at offset sum_{q<p} T_q^2, row-major T_p x T_p)."""
+    lib = require_cuda(x, lengthscale, outputscale, offsets_dev)
+    L = outputscale.shape[1]
+    lo, hi = {"k0": (0, structure.n_comp0), "k1": (structure.n_comp0, structure.n_comp),
+              "all": (0, structure.n_comp)}[which]
+    x = _c(x)
+    P_b = offsets_dev.numel() - 1
+    out = torch.empty(L, int(sum_T2), dtype=F64, device=x.device)
+    ks, keep = make_spec(structure)
+    ls, os_ = _c(lengthscale), _c(outputscale)
+    da = _c(diag_add) if diag_add is not None else None
+    with torch.cuda.device(x.device):
+        rc = lib.lvae_kernel_blocks_f64(C.byref(ks), lo, hi, L, x.shape[1], ptr(x), ptr(offsets_dev), P_b, int(sum_T2),
+                                        ptr(ls), ptr(os_), ptr(da), ptr(out), stream_ptr(x.device))
+    check(rc, "lvae_kernel_blocks_f64")
+    return out
+
+
+def potrf_batched(A, check_info=True):
+    """Lower Cholesky factors of a batch [..., n, n] (torch.cholesky, elbo_functions.py:177,179,185)."""
+    lib = require_cuda(A)
+    out = _c(A).clone()
+    n = out.shape[-1]
+    batch = out.numel() // (n * n)
+    info = torch.zeros(1, dtype=torch.int32, device=out.device)
+    with torch.cuda.device(out.device):
+        rc = lib.lvae_potrf_batched_f64(ptr(out), n, n * n, batch, ptr(info), stream_ptr(out.device))
+    check(rc, "lvae_potrf_batched_f64")
+    if check_info and int(info.item()) != 0:
+        raise RuntimeError(f"cholesky: matrix {int(info.item()) - 1} of the batch is not positive-definite")
+    return out
+
+
+def potri_batched(Lc):
+    """Explicit inverse from a Cholesky factor (cholesky_solve(I, L), elbo_functions.py:178,180,186)."""
+    lib = require_cuda(Lc)
+    Lc = _c(Lc)
+    n = Lc.shape[-1]
+    batch = Lc.numel() // (n * n)
+    out = torch.empty_like(Lc)
+    with torch.cuda.device(Lc.device):
+        rc = lib.lvae_potri_batched_f64(ptr(Lc), ptr(out), n, n * n, batch, stream_ptr(Lc.device))
+    check(rc, "lvae_potri_batched_f64")
+    return out
+
+
+class KldCall:
+    """One prepared call of the KL-bound op: owns outputs/scratch and the C struct (reusable across steps of one shape)."""
+
+    def __init__(self, structure, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=0):
+        self.lib = require_cuda()
+        self.structure, self.device = structure, torch.device(device)
+        self.L, self.M, self.Q, self.P_b, self.N_b = L, M, Q, P_b, N_b
+        dev = self.device
+        e = lambda *s: torch.empty(*s, dtype=F64, device=dev)
+        self.kld_per_latent = e(L)
+        self.grad_m, self.grad_H = e(L, M), e(L, M, M)
+        self.d_mu, self.d_log_v = e(N_b, L), e(N_b, L)
+        self.d_lengthscale, self.d_outputscale, self.d_noise = e(structure.n_ls, L), e(structure.n_comp, L), e(L)
+        self.info = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.ks, self._keep = make_spec(structure)
+        p = KldProblemT()
+        p.L, p.M, p.Q, p.P_b, p.N_b, p.T_max, p.sum_T2 = L, M, Q, P_b, N_b, T_max, int(sum_T2)
+        p.natural_gradient, p.path = int(bool(natural_gradient)), int(path)
+        p.ks = self.ks
+        self.stats_stride = int(self.lib.lvae_kld_stats_stride(M, structure.n_ls, structure.n_comp))
+        self.stats = torch.zeros(L, self.stats_stride, dtype=F64, device=dev)
+        self.workspace = e(int(self.lib.lvae_kld_workspace_doubles(C.byref(p))))
+        for name in ("kld_per_latent", "grad_m", "grad_H", "d_mu", "d_log_v", "d_lengthscale", "d_outputscale",
+                     "d_noise", "stats", "workspace", "info"):
+            setattr(p, name, getattr(self, name).data_ptr())
+        self.p = p
+        self._held = ()
+
+    def bind(self, x, offsets_dev, mu, log_v, z, m, H, lengthscale, outputscale, noise, scale, const_term, eps):
+        held = [_c(t) for t in (x, mu, log_v, z, m, H, lengthscale, outputscale, noise)]
+        p = self.p
+        (p.x, p.mu, p.log_v, p.z, p.m, p.H, p.lengthscale, p.outputscale, p.noise) = [t.data_ptr() for t in held]
+        p.offsets = offsets_dev.data_ptr()
+        p.scale, p.const_term, p.eps = float(scale), float(const_term), float(eps)
+        self._held = (held, offsets_dev)
+        return self
+
+    def _run(self, fn, what):
+        with torch.cuda.device(self.device):
+            check(fn(C.byref(self.p), stream_ptr(self.device)), what)
+
+    def head(self):
+        self._run(self.lib.lvae_kld_head_f64, "lvae_kld_head_f64")
+
+    def subjects(self):
+        self._run(self.lib.lvae_kld_subjects_f64, "lvae_kld_subjects_f64")
+
+    def tail(self):
+        self._run(self.lib.lvae_kld_tail_f64, "lvae_kld_tail_f64")
+
+    def run(self):
+        self._run(self.lib.lvae_kld_minibatch_f64, "lvae_kld_minibatch_f64")
+
+    def raise_on_info(self):
+        info = self.info.tolist()          # one device->host sync, like torch.cholesky's own check
+        names = ("Kzz + eps*I", "H", "a per-subject block K1 + noise*I", "the natural-gradient update")
+        for v, n in zip(info, names):
+            if v:
+                self.info.zero_()
+                raise RuntimeError(f"cholesky: {n} is not positive-definite (flat index {v - 1})")
+
+
+def ng_step(m, H, grad_m, grad_H, lr):
+    """Natural-gradient update of (m [L,M,1], H [L,M,M]) — training.py:129-135.  Returns new detached tensors."""
+    lib = require_cuda(m, H, grad_m, grad_H)
+    L, M = H.shape[0], H.shape[-1]
+    m2, H2 = _c(m).clone(), _c(H).clone()
+    gm, gH = _c(grad_m), _c(grad_H)
+    ws = torch.empty(4 * L * M * M, dtype=F64, device=H.device)
+    info = torch.zeros(4, dtype=torch.int32, device=H.device)
+    with torch.cuda.device(H.device):
+        rc = lib.lvae_ng_step_f64(ptr(m2), ptr(H2), ptr(gm), ptr(gH), float(lr), L, M, ptr(ws), ptr(info),
+                                  stream_ptr(H.device))
+    check(rc, "lvae_ng_step_f64")
+    return m2.view_as(m), H2, info
+
+
+def launch_count():
+    return int(_lib.load().lvae_launch_count())

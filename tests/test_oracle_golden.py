@@ -89,7 +89,7 @@ def test_fixed_T_equals_iter_on_regular_input():
     with torch.no_grad():
         a = orc.kld_fixed_T(k0, k1, t("noise"), L, t("m"), t("H"), t("x"), t("mu"), t("log_v"), t("z"), 15, P_b, T, True, 1e-6)
         b = orc.kld_iter(k0, k1, t("noise"), L, t("m"), t("H"), t("x"), t("mu"), t("log_v"), t("z"), 15, P_b, 15 * T, True, 2, 1e-6)
-    assert abs(a[0].item() - b[0].item()) <= 1e-12 * abs(a[0].item())
+    assert abs(a[0].item() - b[0].item()) <= 1e-9 * abs(a[0].item())
     assert rel(a[1], b[1]) < 1e-9 and rel(a[2], b[2]) < 1e-9
 
 
