@@ -135,6 +135,11 @@ int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream);
 int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, double lr, int32_t L, int32_t M,
                      double* workspace, int32_t* info, void* stream);
 
+/* Optional per-phase device timing with CUDA events on the launch stream (bench.py's roofline leg).
+ * phase: 0 head, 1 prep, 2 subjects, 3 reduce, 4 tail, 5 ng_step.  lvae_profile_last_ms synchronises on the event. */
+int lvae_profile_enable(int on);
+float lvae_profile_last_ms(int phase);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t lvae_launch_count(void);
 const char* lvae_version(void);

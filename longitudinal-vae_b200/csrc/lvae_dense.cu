@@ -199,5 +199,34 @@ extern "C" int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n,
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// per-phase timing
+// ---------------------------------------------------------------------------------------------------------------
+static int g_prof = 0;
+static cudaEvent_t g_ev[LVAE_NPHASE][2];
+static bool g_ev_init = false, g_ev_used[LVAE_NPHASE];
+void lvae_prof_begin(int ph, cudaStream_t st) {
+    if (!g_prof) return;
+    if (!g_ev_init) {
+        for (int i = 0; i < LVAE_NPHASE; ++i) { cudaEventCreate(&g_ev[i][0]); cudaEventCreate(&g_ev[i][1]); g_ev_used[i] = false; }
+        g_ev_init = true;
+    }
+    cudaEventRecord(g_ev[ph][0], st);
+}
+void lvae_prof_end(int ph, cudaStream_t st) {
+    if (!g_prof) return;
+    cudaEventRecord(g_ev[ph][1], st);
+    g_ev_used[ph] = true;
+}
+extern "C" int lvae_profile_enable(int on) { g_prof = on; return 0; }
+// milliseconds of the most recent launch of `phase` (synchronises on its end event); <0 if never recorded
+extern "C" float lvae_profile_last_ms(int ph) {
+    if (ph < 0 || ph >= LVAE_NPHASE || !g_ev_init || !g_ev_used[ph]) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(g_ev[ph][1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g_ev[ph][0], g_ev[ph][1]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
 extern "C" int64_t lvae_launch_count(void) { return lvae_launch_counter(); }
 extern "C" const char* lvae_version(void) { return "lvae_b200 0.1 (sm_100a, fp64)"; }

@@ -8,3 +8,9 @@
 static inline int lvae_cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
 int lvae_make_devspec(const lvae_kernel_spec_t* ks, int Q, DevSpec* out);
 int lvae_block_offsets(const int32_t* offsets, int P_b, int64_t* off2, cudaStream_t st);
+
+// optional per-phase device timing (bench.py's roofline: duration of the dominant kernel measured live with CUDA events
+// on the launch stream).  Phases: 0 head, 1 prep, 2 subjects, 3 reduce, 4 tail, 5 ng_step.
+#define LVAE_NPHASE 6
+void lvae_prof_begin(int phase, cudaStream_t st);
+void lvae_prof_end(int phase, cudaStream_t st);

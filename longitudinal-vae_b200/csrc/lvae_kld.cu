@@ -547,8 +547,10 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     if (rc) return rc;
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
+    lvae_prof_begin(0, (cudaStream_t)stream);
     k_head<<<p->L, 256, 0, (cudaStream_t)stream>>>(sp, w, p->L, p->M, p->Q, p->z, p->m, p->H, p->lengthscale,
                                                    p->outputscale, p->eps, 0.5 * p->scale, p->workspace, p->info);
+    lvae_prof_end(0, (cudaStream_t)stream);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
 }
@@ -572,13 +574,17 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             if (e != cudaSuccess) return lvae_cuda_rc(e);
             prep_attr = s1;
         }
+        lvae_prof_begin(1, st);
         k_prep<<<dim3(w.nchunk, p->L), 128, s1, st>>>(sp, w, p->L, p->Q, p->P_b, Tm, p->x, p->offsets, p->log_v,
                                                       p->lengthscale, p->outputscale, p->noise, c, p->d_log_v,
                                                       p->workspace, p->info);
+        lvae_prof_end(1, st);
         LVAE_COUNT_LAUNCH();
         bool fused = (p->path == 2);
         if (fused) {
+            lvae_prof_begin(2, st);
             rc = lvae_subjects_fused_launch(p, sp, w, st);
+            lvae_prof_end(2, st);
             if (rc) return rc;
         } else {
             const size_t s2 = subj_smem(Tm, p->M, p->Q);
@@ -588,9 +594,11 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
                 if (e != cudaSuccess) return lvae_cuda_rc(e);
                 subj_attr = s2;
             }
+            lvae_prof_begin(2, st);
             k_subjects_generic<<<dim3(w.nchunk, p->L), 256, s2, st>>>(sp, w, p->L, p->M, p->Q, p->P_b, Tm, p->x,
                                                                       p->offsets, p->mu, p->z, p->lengthscale,
                                                                       p->outputscale, c, p->d_mu, p->workspace);
+            lvae_prof_end(2, st);
             LVAE_COUNT_LAUNCH();
         }
     } else {
@@ -599,7 +607,9 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
         e = cudaMemsetAsync(p->workspace + w.ppart, 0, sizeof(double) * ((size_t)w.nchunk * p->L * (LVAE_NSCAL + w.nh)), st);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
     }
+    lvae_prof_begin(3, st);
     k_reduce<<<dim3((unsigned)((w.stride + 255) / 256), p->L), 256, 0, st>>>(w, p->L, p->M, p->workspace, p->stats);
+    lvae_prof_end(3, st);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
 }
@@ -610,10 +620,12 @@ extern "C" int lvae_kld_tail_f64(const lvae_kld_problem_t* p, void* stream) {
     if (rc) return rc;
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
+    lvae_prof_begin(4, (cudaStream_t)stream);
     k_tail<<<p->L, 256, 0, (cudaStream_t)stream>>>(sp, w, p->L, p->M, p->Q, p->natural_gradient, p->z, p->m, p->H,
                                                    p->lengthscale, p->outputscale, 0.5 * p->scale,
                                                    p->const_term / p->L, p->stats, p->workspace, p->kld_per_latent,
                                                    p->grad_m, p->grad_H, p->d_lengthscale, p->d_outputscale, p->d_noise);
+    lvae_prof_end(4, (cudaStream_t)stream);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
 }
@@ -629,7 +641,9 @@ extern "C" int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream)
 extern "C" int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, double lr, int32_t L,
                                 int32_t M, double* workspace, int32_t* info, void* stream) {
     if (L <= 0 || M <= 0 || M > LVAE_MAX_M) return LVAE_E_BADARG;
+    lvae_prof_begin(5, (cudaStream_t)stream);
     k_ng_step<<<L, 256, 0, (cudaStream_t)stream>>>(m, H, grad_m, grad_H, lr, M, workspace, L, info);
+    lvae_prof_end(5, (cudaStream_t)stream);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
 }
