@@ -580,7 +580,7 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
                                                       p->workspace, p->info);
         lvae_prof_end(1, st);
         LVAE_COUNT_LAUNCH();
-        bool fused = (p->path == 2);
+        bool fused = (p->path == 2) || (p->path == 0 && lvae_fused_supported(p));
         if (fused) {
             lvae_prof_begin(2, st);
             rc = lvae_subjects_fused_launch(p, sp, w, st);

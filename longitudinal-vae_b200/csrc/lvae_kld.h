@@ -19,4 +19,5 @@ struct KldLayout {
 KldLayout lvae_layout(const lvae_kld_problem_t* p);
 int lvae_chunks(int P_b, int L);
 // fused DMMA subject pass for M <= 64 (lvae_subjects_fused.cu); fills the same `part` partials as the generic kernel
+bool lvae_fused_supported(const lvae_kld_problem_t* p);
 int lvae_subjects_fused_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
