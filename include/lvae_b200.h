@@ -140,6 +140,9 @@ int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* g
 int lvae_profile_enable(int on);
 float lvae_profile_last_ms(int phase);
 
+/* Test hook: out[i] = the library's exp(x[i]) for x <= 0 (the squared-exponential factor's exp; see lvae_common.cuh). */
+int lvae_debug_exp_neg_f64(const double* x, double* out, int32_t n, void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t lvae_launch_count(void);
 const char* lvae_version(void);

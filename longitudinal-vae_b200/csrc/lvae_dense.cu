@@ -45,9 +45,10 @@ __global__ void __launch_bounds__(256) k_dense(DevSpec sp, int c0, int c1, int Q
                                                int64_t s1, int n1, const double* __restrict__ x2, int64_t s2, int n2,
                                                const double* __restrict__ ls, const double* __restrict__ os, int L,
                                                const double* __restrict__ diag_add, double* __restrict__ out) {
-    __shared__ double hil2[LVAE_MAXC], osc[LVAE_MAXC];
+    __shared__ double hil2[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
     const int b = blockIdx.z, l = b % L;
     const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < LVAE_EXP_TBL) etab[t] = c_exp2_tbl[t];
     if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; hil2[t] = 0.5 / (v * v); }
     if (t < sp.n0 + sp.n1) osc[t] = os[(size_t)t * L + l];
     __syncthreads();
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k_dense(DevSpec sp, int c0, int c1, int Q
     const double* xa = x1 + (size_t)b * s1 + (size_t)i * Q;
     const double* xb = x2 + (size_t)b * s2 + (size_t)j * Q;
     double acc = 0.0, d2;
-    for (int c = c0; c < c1; ++c) acc += osc[c] * comp_value(sp, c, xa, xb, hil2, d2);
+    for (int c = c0; c < c1; ++c) acc += osc[c] * comp_value(sp, c, xa, xb, hil2, d2, etab);
     if (diag_add && i == j) acc += diag_add[l];
     out[((size_t)b * n1 + i) * n2 + j] = acc;
 }
@@ -109,8 +110,9 @@ __global__ void __launch_bounds__(128) k_blocks(DevSpec sp, int c0, int c1, int 
                                                 int64_t block_stride, const double* __restrict__ ls,
                                                 const double* __restrict__ os, int L,
                                                 const double* __restrict__ diag_add, double* __restrict__ out) {
-    __shared__ double hil2[LVAE_MAXC], osc[LVAE_MAXC];
+    __shared__ double hil2[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
     const int p = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
+    if (t < LVAE_EXP_TBL) etab[t] = c_exp2_tbl[t];
     if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; hil2[t] = 0.5 / (v * v); }
     if (t < sp.n0 + sp.n1) osc[t] = os[(size_t)t * L + l];
     __syncthreads();
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(128) k_blocks(DevSpec sp, int c0, int c1, int 
         const double* xa = x + (size_t)(r0 + i) * Q;
         const double* xb = x + (size_t)(r0 + j) * Q;
         double acc = 0.0, d2;
-        for (int c = c0; c < c1; ++c) acc += osc[c] * comp_value(sp, c, xa, xb, hil2, d2);
+        for (int c = c0; c < c1; ++c) acc += osc[c] * comp_value(sp, c, xa, xb, hil2, d2, etab);
         if (diag_add && i == j) acc += diag_add[l];
         o[e] = acc;
     }
@@ -226,6 +228,20 @@ extern "C" float lvae_profile_last_ms(int ph) {
     if (cudaEventSynchronize(g_ev[ph][1]) != cudaSuccess) return -1.f;
     if (cudaEventElapsedTime(&ms, g_ev[ph][0], g_ev[ph][1]) != cudaSuccess) return -1.f;
     return ms;
+}
+
+// test hook: the device exp used by every squared-exponential factor
+__global__ void k_exp_neg(const double* __restrict__ x, double* __restrict__ out, int n) {
+    __shared__ double etab[LVAE_EXP_TBL];
+    load_exp_table(etab);
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = exp_neg(x[i], etab);
+}
+extern "C" int lvae_debug_exp_neg_f64(const double* x, double* out, int32_t n, void* stream) {
+    if (n <= 0) return 0;
+    k_exp_neg<<<(n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
 }
 
 extern "C" int64_t lvae_launch_count(void) { return lvae_launch_counter(); }

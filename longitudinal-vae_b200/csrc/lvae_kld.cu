@@ -13,11 +13,21 @@
 // ---------------------------------------------------------------------------------------------------------------
 // workspace layout
 // ---------------------------------------------------------------------------------------------------------------
-int lvae_chunks(int P_b, int L) {
-    int per_latent = (2 * 148 + L - 1) / L;  // ~2 CTAs per SM over the whole grid
-    if (per_latent < 1) per_latent = 1;
-    if (per_latent > P_b) per_latent = P_b > 0 ? P_b : 1;
-    return per_latent;
+int lvae_chunks(int P_b, int L, int T_max) {
+    // CTAs per latent of the subject pass (one 512-thread CTA per SM): pick the number of waves k that minimises
+    // k * (row groups per CTA + 1 group-equivalent of per-CTA set-up), with L * nchunk <= 148 * k.
+    const int spg = T_max > 0 ? (48 / T_max > 0 ? 48 / T_max : 1) : 1;
+    int best = 1;
+    long best_cost = -1;
+    for (int k = 1; k <= 8; ++k) {
+        int n = 148 * k / L;
+        if (n < 1) continue;
+        if (n > P_b) n = P_b > 0 ? P_b : 1;
+        const int per = (P_b + n - 1) / n;
+        const long cost = (long)k * ((per + spg - 1) / spg + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = n; }
+    }
+    return best;
 }
 
 KldLayout lvae_layout(const lvae_kld_problem_t* p) {
@@ -25,7 +35,8 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     const int64_t L = p->L, M = p->M, MM = M * M;
     w.nh = p->ks.n_ls + p->ks.n_comp0 + p->ks.n_comp1 + 1;
     w.stride = stats_stride((int)M, w.nh);
-    w.nchunk = lvae_chunks(p->P_b, p->L);
+    w.nchunk = lvae_chunks(p->P_b, p->L, p->T_max);
+    w.nprep = lvae_prep_rows(p->P_b, p->L, p->T_max, p->Q);
     int64_t o = 0;
     w.Ki = o; o += L * MM;
     w.Hi = o; o += L * MM;
@@ -39,7 +50,7 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.Bi = o; o += L * p->sum_T2;
     w.off2 = o; o += (int64_t)p->P_b + 1;
     w.part = o; o += (int64_t)w.nchunk * L * w.stride;   // subject partials (S, ng1, da, A, hyp)
-    w.ppart = o; o += (int64_t)w.nchunk * L * (LVAE_NSCAL + w.nh);   // prep partials (scalars, hyp)
+    w.ppart = o; o += (int64_t)w.nprep * L * (LVAE_NSCAL + w.nh);   // prep partials (scalars, hyp)
     w.total = o;
     return w;
 }
@@ -62,6 +73,7 @@ struct LatentHyp {
     double il3[LVAE_MAXC];    // 1 / l^3
     double os[LVAE_MAXC];
     double noise;
+    double etab[LVAE_EXP_TBL];
 };
 __device__ inline void load_hyp(LatentHyp* h, const DevSpec& sp, const double* ls, const double* os, const double* noise,
                                 int L, int l) {
@@ -69,6 +81,7 @@ __device__ inline void load_hyp(LatentHyp* h, const DevSpec& sp, const double* l
     if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; h->hil2[t] = 0.5 / (v * v); h->il3[t] = 1.0 / (v * v * v); }
     if (t < sp.n0 + sp.n1) h->os[t] = os[(size_t)t * L + l];
     if (t == 0) h->noise = noise ? noise[l] : 0.0;
+    load_exp_table(h->etab);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -96,7 +109,7 @@ __global__ void __launch_bounds__(256) k_head(DevSpec sp, KldLayout w, int L, in
     for (int e = tid; e < MM; e += nt) {
         const int i = e / M, j = e % M;
         double acc = 0.0, d2;
-        for (int cc = 0; cc < sp.n0; ++cc) acc += hyp.os[cc] * comp_value(sp, cc, zl + i * Q, zl + j * Q, hyp.hil2, d2);
+        for (int cc = 0; cc < sp.n0; ++cc) acc += hyp.os[cc] * comp_value(sp, cc, zl + i * Q, zl + j * Q, hyp.hil2, d2, hyp.etab);
         T1[e] = acc + (i == j ? eps : 0.0);
     }
     __syncthreads();
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(128) k_prep(DevSpec sp, KldLayout w, int L, in
             const int i = e / T, j = e % T;
             double k0 = 0.0, k1 = 0.0, d2;
             for (int cc = 0; cc < nc; ++cc) {
-                const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hyp.hil2, d2);
+                const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hyp.hil2, d2, hyp.etab);
                 fc[(size_t)cc * TT + e] = f;
                 if (cc < sp.n0) k0 += hyp.os[cc] * f; else k1 += hyp.os[cc] * f;
             }
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(256) k_subjects_generic(DevSpec sp, KldLayout 
         for (int e = tid; e < T * M; e += nt) {                    // Kxz_p (elbo_functions.py:171)
             const int t = e / M, j = e % M;
             double k0 = 0.0, d2;
-            for (int cc = 0; cc < sp.n0; ++cc) k0 += hyp.os[cc] * comp_value(sp, cc, xs + t * Q, zs + j * Q, hyp.hil2, d2);
+            for (int cc = 0; cc < sp.n0; ++cc) k0 += hyp.os[cc] * comp_value(sp, cc, xs + t * Q, zs + j * Q, hyp.hil2, d2, hyp.etab);
             Kx[e] = k0;
         }
         __syncthreads();
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(256) k_subjects_generic(DevSpec sp, KldLayout 
             const double gbar = 2.0 * c * u[t] * av[j] + 2.0 * y;
             for (int cc = 0; cc < sp.n0; ++cc) {
                 double d2;
-                const double f = comp_value(sp, cc, xs + t * Q, zs + j * Q, hyp.hil2, d2);
+                const double f = comp_value(sp, cc, xs + t * Q, zs + j * Q, hyp.hil2, d2, hyp.etab);
                 acc[1 + sp.n_ls + cc] += gbar * f;
                 if (sp.rbf_dim[cc] >= 0) acc[1 + sp.ls_idx[cc]] += gbar * hyp.os[cc] * f * d2 * hyp.il3[sp.ls_idx[cc]];
             }
@@ -330,7 +343,7 @@ __global__ void __launch_bounds__(256) k_subjects_generic(DevSpec sp, KldLayout 
             const double gB = -(c * u[i] * u[j] + q);
             for (int cc = sp.n0; cc < sp.n0 + sp.n1; ++cc) {
                 double d2;
-                const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hyp.hil2, d2);
+                const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hyp.hil2, d2, hyp.etab);
                 acc[1 + sp.n_ls + cc] += gB * f;
                 if (sp.rbf_dim[cc] >= 0) acc[1 + sp.ls_idx[cc]] += gB * hyp.os[cc] * f * d2 * hyp.il3[sp.ls_idx[cc]];
             }
@@ -364,7 +377,7 @@ __global__ void __launch_bounds__(256) k_reduce(KldLayout w, int L, int M, const
     for (int ch = 0; ch < w.nchunk; ++ch) s += ws[w.part + ((size_t)ch * L + l) * w.stride + k];
     const int64_t ks = k - stats_off_scal(M);
     if (ks >= 0) {   // scalars and hyper-gradients also receive the prep partials
-        for (int ch = 0; ch < w.nchunk; ++ch) s += ws[w.ppart + ((size_t)ch * L + l) * (LVAE_NSCAL + w.nh) + ks];
+        for (int ch = 0; ch < w.nprep; ++ch) s += ws[w.ppart + ((size_t)ch * L + l) * (LVAE_NSCAL + w.nh) + ks];
     }
     stats[(size_t)l * w.stride + k] = s;
 }
@@ -466,7 +479,7 @@ __global__ void __launch_bounds__(256) k_tail(DevSpec sp, KldLayout w, int L, in
         const double gK = -0.5 * (T3[i * M + j] + T3[j * M + i]) + 0.5 * Ki[e];
         for (int cc = 0; cc < sp.n0; ++cc) {
             double dd;
-            const double f = comp_value(sp, cc, zl + i * Q, zl + j * Q, hyp.hil2, dd);
+            const double f = comp_value(sp, cc, zl + i * Q, zl + j * Q, hyp.hil2, dd, hyp.etab);
             acc[sp.n_ls + cc] += gK * f;
             if (sp.rbf_dim[cc] >= 0) acc[sp.ls_idx[cc]] += gK * hyp.os[cc] * f * dd * hyp.il3[sp.ls_idx[cc]];
         }
@@ -575,11 +588,16 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             prep_attr = s1;
         }
         lvae_prof_begin(1, st);
-        k_prep<<<dim3(w.nchunk, p->L), 128, s1, st>>>(sp, w, p->L, p->Q, p->P_b, Tm, p->x, p->offsets, p->log_v,
-                                                      p->lengthscale, p->outputscale, p->noise, c, p->d_log_v,
-                                                      p->workspace, p->info);
+        if (p->path != 1 && lvae_prep_warp_supported(p)) {
+            rc = lvae_prep_warp_launch(p, sp, w, st);
+            if (rc) return rc;
+        } else {
+            k_prep<<<dim3(w.nprep, p->L), 128, s1, st>>>(sp, w, p->L, p->Q, p->P_b, Tm, p->x, p->offsets, p->log_v,
+                                                         p->lengthscale, p->outputscale, p->noise, c, p->d_log_v,
+                                                         p->workspace, p->info);
+            LVAE_COUNT_LAUNCH();
+        }
         lvae_prof_end(1, st);
-        LVAE_COUNT_LAUNCH();
         bool fused = (p->path == 2) || (p->path == 0 && lvae_fused_supported(p));
         if (fused) {
             lvae_prof_begin(2, st);
@@ -604,7 +622,7 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
     } else {
         cudaError_t e = cudaMemsetAsync(p->workspace + w.part, 0, sizeof(double) * ((size_t)w.nchunk * p->L * w.stride), st);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
-        e = cudaMemsetAsync(p->workspace + w.ppart, 0, sizeof(double) * ((size_t)w.nchunk * p->L * (LVAE_NSCAL + w.nh)), st);
+        e = cudaMemsetAsync(p->workspace + w.ppart, 0, sizeof(double) * ((size_t)w.nprep * p->L * (LVAE_NSCAL + w.nh)), st);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
     }
     lvae_prof_begin(3, st);

@@ -13,11 +13,15 @@ struct KldLayout {
     int64_t ppart;                      // [nchunk, L, NSCAL+nh] per-CTA partials of the prep pass
     int64_t total;
     int64_t stride;                     // statistics row length
-    int nh, nchunk;
+    int nh, nchunk;                     // nchunk: CTAs per latent of the subject pass
+    int nprep;                          // partial rows per latent of the prep pass
 };
 
 KldLayout lvae_layout(const lvae_kld_problem_t* p);
-int lvae_chunks(int P_b, int L);
+int lvae_chunks(int P_b, int L, int T_max);
+int lvae_prep_rows(int P_b, int L, int T_max, int Q);
+bool lvae_prep_warp_supported(const lvae_kld_problem_t* p);
+int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
 // fused DMMA subject pass for M <= 64 (lvae_subjects_fused.cu); fills the same `part` partials as the generic kernel
 bool lvae_fused_supported(const lvae_kld_problem_t* p);
 int lvae_subjects_fused_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);

@@ -1,0 +1,296 @@
+// Per-subject T x T work of the GP-prior ELBO path, one WARP per (subject, latent) task, no block barriers:
+//   B_p = K1(X_p, X_p) + s2 I  ->  Cholesky (in place)  ->  L^-1  ->  B_p^-1 = L^-T L^-1   (elbo_functions.py:174,179-180)
+//   K0_p (173), scalars C = 2 sum log L_tt (192), D1 = sum B^-1 o K0 (193), Bt = sum (B^-1)_tt e^{logv} (191), F (196),
+//   d_log_v, and the part of the reverse pass that only needs T x T blocks:
+//     adjoint of K0_p = c B^-1 ;  local adjoint of B_p = c (B^-1 - B^-1 (diag(v) + K0_p) B^-1)
+//   contracted with d k_c / d theta on the fly (component entries are never stored).
+// The three T x T products run on the FP64 tensor pipe (DMMA.8x8x4); the three T x T scratch matrices of a warp live in
+// shared memory with a row stride = 4 or 12 (mod 16) doubles, which makes every DMMA fragment load conflict-free.
+// B_p^-1 is written to the workspace for the fused subject pass.  Partial sums are kept per lane in registers over all
+// tasks of the warp and written once (deterministic fixed-order reduction in k_reduce).
+#include "lvae_kld.h"
+
+namespace {
+
+constexpr int PWMAX = 8;     // warps per CTA (fewer when the per-warp scratch of a large T does not fit)
+constexpr int NCMAX = 8;     // components (K0 + K1) handled by the register accumulators
+constexpr int NT8MAX = 5;    // T <= 40
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C[i][j] (i,j < T) = sum_k A(i,k) B(k,j) for row-major operands in smem; TA: A(i,k) = A[k][i].  Output row by row of
+// 8x8 tiles; `sym`: only tiles tj <= ti are computed and mirrored.
+// (i, j) of the e-th element of the lower triangle (row-major, j <= i)
+__device__ __forceinline__ void tri_index(int e, int& i, int& j) {
+    i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    while (i * (i + 1) / 2 > e) --i;
+    j = e - i * (i + 1) / 2;
+}
+
+template <bool TA, bool SYM>
+__device__ __forceinline__ void warp_mm(const double* __restrict__ A, const double* __restrict__ B,
+                                        double* __restrict__ C, int T, int ld, int nt8, int nk4, int g, int q) {
+    for (int ti = 0; ti < nt8; ++ti) {
+        double acc[NT8MAX][2];
+#pragma unroll
+        for (int tj = 0; tj < NT8MAX; ++tj) acc[tj][0] = acc[tj][1] = 0.0;
+        const int tjmax = SYM ? ti + 1 : nt8;
+        for (int ks = 0; ks < nk4; ++ks) {
+            const double a = TA ? A[(4 * ks + q) * ld + 8 * ti + g] : A[(8 * ti + g) * ld + 4 * ks + q];
+#pragma unroll
+            for (int tj = 0; tj < NT8MAX; ++tj) {
+                if (tj < tjmax) {
+                    const double b = B[(4 * ks + q) * ld + 8 * tj + g];
+                    dmma(acc[tj][0], acc[tj][1], a, b);
+                }
+            }
+        }
+        const int i = 8 * ti + g;
+#pragma unroll
+        for (int tj = 0; tj < NT8MAX; ++tj) {
+            if (tj < tjmax) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * tj + 2 * q + e;
+                    if (i < T && j < T) {
+                        C[i * ld + j] = acc[tj][e];
+                        if (SYM && tj < ti) C[j * ld + i] = acc[tj][e];
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PWMAX * 32)
+k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int Tmax, int ld,
+            const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ log_v,
+            const double* __restrict__ ls, const double* __restrict__ os, const double* __restrict__ noise, double c,
+            double* __restrict__ d_log_v, double* __restrict__ ws, int32_t* info) {
+    extern __shared__ double sm[];
+    __shared__ double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
+    __shared__ double s_noise;
+    const int l = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int nc = sp.n0 + sp.n1, nh = hyp_count(sp);
+    if (tid < sp.n_ls) { const double v = ls[(size_t)tid * L + l]; hil2[tid] = 0.5 / (v * v); il3[tid] = 1.0 / (v * v * v); }
+    if (tid < nc) osc[tid] = os[(size_t)tid * L + l];
+    if (tid == 0) s_noise = noise[l];
+    load_exp_table(etab);
+    const int TP8 = (Tmax + 7) & ~7;
+    const int asz = TP8 * ld;
+    double* A1 = sm + (size_t)wid * (3 * asz + Tmax * Q + Tmax);
+    double* A2 = A1 + asz;
+    double* A3 = A2 + asz;
+    double* xs = A3 + asz;
+    double* ev = xs + Tmax * Q;
+    for (int e = lane; e < 3 * asz; e += 32) A1[e] = 0.0;
+    __syncthreads();
+    const int64_t* off2 = reinterpret_cast<const int64_t*>(ws + w.off2);
+
+    double sC = 0.0, sD1 = 0.0, sBt = 0.0, sF = 0.0, gno = 0.0;
+    double gos[NCMAX], gls[NCMAX];
+#pragma unroll
+    for (int k = 0; k < NCMAX; ++k) gos[k] = gls[k] = 0.0;
+
+    const int PW = blockDim.x >> 5;
+    const int nwarps = gridDim.x * PW, gw = blockIdx.x * PW + wid;
+    int Tprev = -1;
+    for (int p = gw; p < P_b; p += nwarps) {
+        const int r0 = offsets[p], T = offsets[p + 1] - r0;
+        const int nt8 = (T + 7) >> 3, nk4 = (T + 3) >> 2;
+        __syncwarp();
+        if (Tprev != -1 && T != Tprev) {          // ragged batches: restore the zero padding the DMMA tiles rely on
+            for (int e = lane; e < 3 * asz; e += 32) A1[e] = 0.0;
+        }
+        Tprev = T;
+        for (int e = lane; e < T * Q; e += 32) xs[e] = x[(size_t)r0 * Q + e];
+        for (int t = lane; t < T; t += 32) {
+            const double lv = log_v[(size_t)(r0 + t) * L + l];
+            ev[t] = exp(lv);
+            sF += lv;
+        }
+        __syncwarp();
+        // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) -------------------------------------------------
+        const int ntri = T * (T + 1) / 2;
+        for (int e = lane; e < ntri; e += 32) {
+            int i, j;
+            tri_index(e, i, j);
+            double k1 = 0.0, d2;
+            for (int cc = sp.n0; cc < nc; ++cc) k1 += osc[cc] * comp_value(sp, cc, xs + i * Q, xs + j * Q, hil2, d2, etab);
+            if (i == j) k1 += s_noise;
+            A1[i * ld + j] = k1;
+            A1[j * ld + i] = k1;
+        }
+        __syncwarp();
+        // ---- Cholesky in place (right-looking, warp-synchronous) ----------------------------------------------------
+        for (int k = 0; k < T; ++k) {
+            const double dkk = A1[k * ld + k];
+            if (!(dkk > 0.0)) { if (lane == 0) atomicCAS(info + 2, 0, l * P_b + p + 1); }
+            const double d = sqrt(dkk), inv = 1.0 / d;
+            __syncwarp();
+            for (int i = k + lane; i < T; i += 32) A1[i * ld + k] = (i == k) ? d : A1[i * ld + k] * inv;
+            __syncwarp();
+            for (int i = k + 1 + lane; i < T; i += 32) {
+                const double lik = A1[i * ld + k];
+                for (int j = k + 1; j <= i; ++j) A1[i * ld + j] -= lik * A1[j * ld + k];
+            }
+            __syncwarp();
+        }
+        for (int t = lane; t < T; t += 32) sC += 2.0 * log(A1[t * ld + t]);                                   // 192
+        // ---- L^-1 (lane per column, forward substitution) into A2 ----------------------------------------------------
+        for (int j = lane; j < T; j += 32) {
+            for (int i = 0; i < j; ++i) A2[i * ld + j] = 0.0;
+            A2[j * ld + j] = 1.0 / A1[j * ld + j];
+            for (int i = j + 1; i < T; ++i) {
+                double s0 = 0.0, s1 = 0.0;
+                int k = j;
+                for (; k + 1 < i; k += 2) { s0 += A1[i * ld + k] * A2[k * ld + j]; s1 += A1[i * ld + k + 1] * A2[(k + 1) * ld + j]; }
+                if (k < i) s0 += A1[i * ld + k] * A2[k * ld + j];
+                A2[i * ld + j] = -(s0 + s1) / A1[i * ld + i];
+            }
+        }
+        __syncwarp();
+        // ---- B^-1 = L^-T L^-1 into A3 --------------------------------------------------------------------------------
+        warp_mm<true, true>(A2, A2, A3, T, ld, nt8, nk4, g, q);
+        __syncwarp();
+        // ---- K0_p (+ diag v) into A1 ; D1 ; adjoint of K0 = c B^-1 contracted on the fly (lower triangle, weight 2) ---
+        for (int e = lane; e < ntri; e += 32) {
+            int i, j;
+            tri_index(e, i, j);
+            const double bi = A3[i * ld + j] * (i == j ? 1.0 : 2.0);
+            double k0 = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < NCMAX; ++cc) {
+                if (cc < sp.n0) {
+                    double d2;
+                    const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hil2, d2, etab);
+                    k0 += osc[cc] * f;
+                    gos[cc] += bi * f;
+                    if (sp.rbf_dim[cc] >= 0) gls[cc] += bi * f * d2;
+                }
+            }
+            sD1 += bi * k0;
+            A1[i * ld + j] = k0 + (i == j ? ev[i] : 0.0);
+            A1[j * ld + i] = A1[i * ld + j];
+        }
+        __syncwarp();
+        // ---- X1 = (diag v + K0) B^-1 -> A2 ; X2 = B^-1 X1 -> A1 -------------------------------------------------------
+        warp_mm<false, false>(A1, A3, A2, T, ld, nt8, nk4, g, q);
+        __syncwarp();
+        warp_mm<false, false>(A3, A2, A1, T, ld, nt8, nk4, g, q);
+        __syncwarp();
+        // ---- B^-1 out ; local adjoint of B_p: (B^-1 - X2) [times c at the end] ; K1 hyper-gradients ; Bt ; d_log_v -------
+        {
+            double* gBi = ws + w.Bi + (size_t)l * w.Bi_stride + off2[p];
+            int i = 0, j = lane;
+            while (j >= T) { j -= T; ++i; }
+            for (int e = lane; e < T * T; e += 32) {
+                gBi[e] = A3[i * ld + j];
+                j += 32;
+                while (j >= T) { j -= T; ++i; }
+            }
+        }
+        for (int e = lane; e < ntri; e += 32) {
+            int i, j;
+            tri_index(e, i, j);
+            const double bi = A3[i * ld + j];
+            const double gB = (i == j) ? bi - A1[i * ld + i] : 2.0 * bi - (A1[i * ld + j] + A1[j * ld + i]);
+#pragma unroll
+            for (int cc = 0; cc < NCMAX; ++cc) {
+                if (cc >= sp.n0 && cc < nc) {
+                    double d2;
+                    const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hil2, d2, etab);
+                    gos[cc] += gB * f;
+                    if (sp.rbf_dim[cc] >= 0) gls[cc] += gB * f * d2;
+                }
+            }
+            if (i == j) {
+                gno += gB;
+                const double bt = bi * ev[i];
+                sBt += bt;
+                d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
+            }
+        }
+    }
+    // ---- per-warp partial row ---------------------------------------------------------------------------------------
+    double* out = ws + w.ppart + ((size_t)gw * L + l) * (LVAE_NSCAL + nh);
+    sC = warp_sum(sC); sD1 = warp_sum(sD1); sBt = warp_sum(sBt); sF = warp_sum(sF); gno = warp_sum(gno);
+    if (lane == 0) {
+        for (int k = 0; k < LVAE_NSCAL + nh; ++k) out[k] = 0.0;
+        out[SC_C] = sC; out[SC_D1] = sD1; out[SC_BT] = sBt; out[SC_F] = sF;
+        out[LVAE_NSCAL + nh - 1] = c * gno;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < NCMAX; ++cc) {
+        if (cc < nc) {
+            const double a = warp_sum(gos[cc]);
+            const double b = warp_sum(gls[cc]);
+            if (lane == 0) {
+                out[LVAE_NSCAL + sp.n_ls + cc] = c * a;
+                // several components may share no lengthscale row; each SE component owns its row (spec.py)
+                if (sp.rbf_dim[cc] >= 0) out[LVAE_NSCAL + sp.ls_idx[cc]] += c * b * osc[cc] * il3[sp.ls_idx[cc]];
+            }
+        }
+    }
+}
+
+} // namespace
+
+static int ld_for(int Tmax) {
+    int ld = (Tmax + 3) & ~3;
+    while (ld % 16 != 4 && ld % 16 != 12) ++ld;
+    return ld;
+}
+
+static size_t warp_doubles(int Tm, int Q) {
+    const int ld = ld_for(Tm), TP8 = (Tm + 7) & ~7;
+    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + Tm;
+}
+
+static int warps_per_cta(int Tm, int Q) {
+    int pw = (int)((200 * 1024) / (sizeof(double) * warp_doubles(Tm, Q)));
+    if (pw > PWMAX) pw = PWMAX;
+    return pw < 1 ? 1 : pw;
+}
+
+int lvae_prep_rows(int P_b, int L, int T_max, int Q) {
+    // partial rows per latent = warps per latent: about one wave of CTAs, a few tasks per warp
+    const int Tm = T_max > 0 ? T_max : 1;
+    const int pw = warps_per_cta(Tm, Q);
+    const size_t cta_bytes = sizeof(double) * pw * warp_doubles(Tm, Q) + 2048;
+    int per_sm = (int)((227 * 1024) / cta_bytes);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * pw > 32) per_sm = 32 / pw > 0 ? 32 / pw : 1;
+    int ctas = per_sm * 148 / L;
+    if (ctas < 1) ctas = 1;
+    const int need = (P_b + pw - 1) / pw;
+    if (ctas > need) ctas = need > 0 ? need : 1;
+    return ctas * pw;
+}
+
+bool lvae_prep_warp_supported(const lvae_kld_problem_t* p) {
+    return p->ks.n_comp0 + p->ks.n_comp1 <= NCMAX && p->T_max <= 8 * NT8MAX;
+}
+
+int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    const int Tm = p->T_max > 0 ? p->T_max : 1;
+    const int ld = ld_for(Tm);
+    const int pw = warps_per_cta(Tm, p->Q);
+    const size_t smem = sizeof(double) * (size_t)pw * warp_doubles(Tm, p->Q);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_prep_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return lvae_cuda_rc(e);
+        attr = smem;
+    }
+    k_prep_warp<<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, Tm, ld, p->x, p->offsets,
+                                                                p->log_v, p->lengthscale, p->outputscale, p->noise,
+                                                                0.5 * p->scale, p->d_log_v, p->workspace, p->info);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}

@@ -63,7 +63,7 @@ k_subjects_fused(const __grid_constant__ DevSpec sp, const __grid_constant__ Kld
                  const double* __restrict__ z, const double* __restrict__ ls, const double* __restrict__ os, double c,
                  double* __restrict__ d_mu, double* __restrict__ ws) {
     extern __shared__ double sm[];
-    __shared__ double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC];
+    __shared__ double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
     const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
     const int wid = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int nh = hyp_count(sp), MM = M * M;
@@ -94,6 +94,7 @@ k_subjects_fused(const __grid_constant__ DevSpec sp, const __grid_constant__ Kld
     // ---- per-CTA constants ---------------------------------------------------------------------------------------
     if (tid < sp.n_ls) { const double v = ls[(size_t)tid * L + l]; hil2[tid] = 0.5 / (v * v); il3[tid] = 1.0 / (v * v * v); }
     if (tid < sp.n0 + sp.n1) osc[tid] = os[(size_t)tid * L + l];
+    load_exp_table(etab);
     {
         const double* Wl = ws + w.W + (size_t)l * MM;
         for (int e = tid; e < 64 * LD; e += 512) {
@@ -169,7 +170,7 @@ k_subjects_fused(const __grid_constant__ DevSpec sp, const __grid_constant__ Kld
 #pragma unroll
                 for (int cc = 0; cc < NC0; ++cc) {
                     double d2, f = 0.0;
-                    if (valid) f = comp_value(sp, cc, xs + t * Q, zs + j * Q, hil2, d2);
+                    if (valid) f = comp_value(sp, cc, xs + t * Q, zs + j * Q, hil2, d2, etab);
                     fc[i][e][cc] = f;
                     kx[e] += osc[cc] * f;
                 }
@@ -322,7 +323,7 @@ k_subjects_fused(const __grid_constant__ DevSpec sp, const __grid_constant__ Kld
                                 if (k < sp.n1) {
                                     const int cc = sp.n0 + k;
                                     double d2;
-                                    const double f = comp_value(sp, cc, xs + t * Q, xs + t2 * Q, hil2, d2);
+                                    const double f = comp_value(sp, cc, xs + t * Q, xs + t2 * Q, hil2, d2, etab);
                                     g1os[k] += gB * f;
                                     if (sp.rbf_dim[cc] >= 0) g1ls[k] += gB * f * d2;
                                 }

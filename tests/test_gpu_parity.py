@@ -195,3 +195,21 @@ def test_fresh_seeded_inputs_vs_oracle(cfg, P, L, M):
     assert abs(out[0].item() - ref[0].item()) <= TOL * abs(ref[0].item())
     assert rel(out[1], ref[1]) < TOL and rel(out[2], ref[2]) < TOL
     assert rel(mu.grad, mu_o.grad) < TOL
+
+
+def test_device_exp_accuracy():
+    """The library's exp for non-positive arguments (every SE factor goes through it) against numpy: <= 2 ulp."""
+    from lvae_b200 import _lib
+    lib = _lib.require_cuda()
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([-torch.rand(200000, generator=g, dtype=torch.float64) * 60,
+                   -torch.rand(50000, generator=g, dtype=torch.float64) * 700,
+                   -torch.rand(50000, generator=g, dtype=torch.float64) * 1e-3,
+                   torch.tensor([0.0, -0.0, -1e-300, -700.0, -745.0, -1e6], dtype=torch.float64)]).cuda()
+    out = torch.empty_like(x)
+    _lib.check(lib.lvae_debug_exp_neg_f64(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr()), "exp")
+    ref = np.exp(x.cpu().numpy())
+    got = out.cpu().numpy()
+    big = ref > 1e-300
+    assert np.abs(got[big] - ref[big]).max() / 1.0 >= 0 and (np.abs(got[big] - ref[big]) / ref[big]).max() < 4.5e-16
+    assert np.all(got[~big] <= 1e-300) and np.all(got >= 0)
