@@ -261,8 +261,9 @@ def main():
         if dist is not None:
             dist.all_reduce(call.stats)
         call.tail()
-        rc = lib.lvae_ng_step_f64(_lib.ptr(m), _lib.ptr(H), _lib.ptr(call.grad_m), _lib.ptr(call.grad_H), lr, L, M,
-                                  _lib.ptr(ng_ws), _lib.ptr(ng_info), _lib.stream_ptr(device))
+        rc = lib.lvae_ng_step_f64(_lib.ptr(m), _lib.ptr(H), _lib.ptr(call.grad_m), _lib.ptr(call.grad_H),
+                                  _lib.ptr(call.Hinv), lr, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
+                                  _lib.stream_ptr(device))
         _lib.check(rc, "lvae_ng_step_f64")
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)   # > 126 MB L2
@@ -361,8 +362,9 @@ def main():
         def small():
             c2.bind(x[:rows], off2, mu[:rows], lv[:rows], z, mm.view(L, M), HH, ls, os_, noise, P_tot / spb2, const, 1e-6)
             c2.run()
-            lib.lvae_ng_step_f64(_lib.ptr(mm), _lib.ptr(HH), _lib.ptr(c2.grad_m), _lib.ptr(c2.grad_H), lr, L, M,
-                                 _lib.ptr(ng_ws), _lib.ptr(ng_info), _lib.stream_ptr(device))
+            lib.lvae_ng_step_f64(_lib.ptr(mm), _lib.ptr(HH), _lib.ptr(c2.grad_m), _lib.ptr(c2.grad_H),
+                                 _lib.ptr(c2.Hinv), lr, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
+                                 _lib.stream_ptr(device))
         for _ in range(5):
             small()
         torch.cuda.synchronize()

@@ -131,9 +131,12 @@ int lvae_kld_tail_f64(const lvae_kld_problem_t* p, void* stream);
 /* head + subjects + tail on one GPU */
 int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream);
 
-/* Natural-gradient update of (m, H), in place (training.py:129-135).  workspace: 4*L*M*M doubles; info[3]. */
-int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, double lr, int32_t L, int32_t M,
-                     double* workspace, int32_t* info, void* stream);
+/* Natural-gradient update of (m, H), in place (training.py:129-135).  Hinv: optional [L,M,M] H^-1 already computed by
+ * lvae_kld_head_f64 for the same H (at workspace + lvae_kld_hinv_offset()); NULL recomputes it (training.py:130-131).
+ * workspace: 4*L*M*M doubles (used for M > 64 only); info[3]. */
+int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hinv, double lr,
+                     int32_t L, int32_t M, double* workspace, int32_t* info, void* stream);
+int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p);
 
 /* Optional per-phase device timing with CUDA events on the launch stream (bench.py's roofline leg).
  * phase: 0 head, 1 prep, 2 subjects, 3 reduce, 4 tail, 5 ng_step.  lvae_profile_last_ms synchronises on the event. */

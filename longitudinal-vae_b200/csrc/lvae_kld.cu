@@ -561,6 +561,11 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
     lvae_prof_begin(0, (cudaStream_t)stream);
+    if (p->M <= 64 && p->path != 1) {
+        rc = lvae_head64_launch(p, sp, w, (cudaStream_t)stream);
+        lvae_prof_end(0, (cudaStream_t)stream);
+        return rc;
+    }
     k_head<<<p->L, 256, 0, (cudaStream_t)stream>>>(sp, w, p->L, p->M, p->Q, p->z, p->m, p->H, p->lengthscale,
                                                    p->outputscale, p->eps, 0.5 * p->scale, p->workspace, p->info);
     lvae_prof_end(0, (cudaStream_t)stream);
@@ -639,6 +644,11 @@ extern "C" int lvae_kld_tail_f64(const lvae_kld_problem_t* p, void* stream) {
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
     lvae_prof_begin(4, (cudaStream_t)stream);
+    if (p->M <= 64 && p->path != 1) {
+        rc = lvae_tail64_launch(p, sp, w, (cudaStream_t)stream);
+        lvae_prof_end(4, (cudaStream_t)stream);
+        return rc;
+    }
     k_tail<<<p->L, 256, 0, (cudaStream_t)stream>>>(sp, w, p->L, p->M, p->Q, p->natural_gradient, p->z, p->m, p->H,
                                                    p->lengthscale, p->outputscale, 0.5 * p->scale,
                                                    p->const_term / p->L, p->stats, p->workspace, p->kld_per_latent,
@@ -656,10 +666,17 @@ extern "C" int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream)
     return lvae_kld_tail_f64(p, stream);
 }
 
-extern "C" int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, double lr, int32_t L,
-                                int32_t M, double* workspace, int32_t* info, void* stream) {
+extern "C" int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p) { return lvae_layout(p).Hi; }
+
+extern "C" int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hinv,
+                                double lr, int32_t L, int32_t M, double* workspace, int32_t* info, void* stream) {
     if (L <= 0 || M <= 0 || M > LVAE_MAX_M) return LVAE_E_BADARG;
     lvae_prof_begin(5, (cudaStream_t)stream);
+    if (M <= 64) {
+        const int rc = lvae_ng64_launch(m, H, grad_m, grad_H, Hinv, lr, L, M, info, (cudaStream_t)stream);
+        lvae_prof_end(5, (cudaStream_t)stream);
+        return rc;
+    }
     k_ng_step<<<L, 256, 0, (cudaStream_t)stream>>>(m, H, grad_m, grad_H, lr, M, workspace, L, info);
     lvae_prof_end(5, (cudaStream_t)stream);
     LVAE_COUNT_LAUNCH();

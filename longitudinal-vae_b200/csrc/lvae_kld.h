@@ -25,3 +25,9 @@ int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const 
 // fused DMMA subject pass for M <= 64 (lvae_subjects_fused.cu); fills the same `part` partials as the generic kernel
 bool lvae_fused_supported(const lvae_kld_problem_t* p);
 int lvae_subjects_fused_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+
+// M <= 64 shared-memory kernels (lvae_kld64.cu)
+int lvae_head64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+int lvae_tail64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+int lvae_ng64_launch(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hi, double lr, int L,
+                     int M, int32_t* info, cudaStream_t st);

@@ -55,6 +55,8 @@ class _KldBound(torch.autograd.Function):
         ctx.ng = meta["natural_gradient"]
         ctx.mshape = m.shape
         ctx.mark_non_differentiable(call.grad_m, call.grad_H)
+        # H^-1 of the head kernel rides along for natural_gradient_step (training.py:130-131 recomputes it)
+        meta["Hinv"] = (call.Hinv, H.data_ptr(), H._version)
         return kld, call.grad_m.view(L, M, 1), call.grad_H
 
     @staticmethod
@@ -84,6 +86,7 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
                 scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient))
     kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), ls, os_, noise, meta)
     if natural_gradient:
+        gH._lvae_hinv = meta.get("Hinv")
         return kld, gm, gH
     return kld, None, None
 

@@ -114,6 +114,8 @@ class KldCall:
             setattr(p, name, getattr(self, name).data_ptr())
         self.p = p
         self._held = ()
+        off = int(self.lib.lvae_kld_hinv_offset(C.byref(p)))
+        self.Hinv = self.workspace[off:off + L * M * M].view(L, M, M)      # H^-1 left by the head kernel
 
     def bind(self, x, offsets_dev, mu, log_v, z, m, H, lengthscale, outputscale, noise, scale, const_term, eps):
         held = [_c(t) for t in (x, mu, log_v, z, m, H, lengthscale, outputscale, noise)]
@@ -149,16 +151,18 @@ class KldCall:
                 raise RuntimeError(f"cholesky: {n} is not positive-definite (flat index {v - 1})")
 
 
-def ng_step(m, H, grad_m, grad_H, lr):
-    """Natural-gradient update of (m [L,M,1], H [L,M,M]) — training.py:129-135.  Returns new detached tensors."""
+def ng_step(m, H, grad_m, grad_H, lr, Hinv=None):
+    """Natural-gradient update of (m [L,M,1], H [L,M,M]) — training.py:129-135.  Returns new detached tensors.
+    Hinv: H^-1 already computed by the bound's head kernel for this H (saves one Cholesky + inverse)."""
     lib = require_cuda(m, H, grad_m, grad_H)
     L, M = H.shape[0], H.shape[-1]
     m2, H2 = _c(m).clone(), _c(H).clone()
     gm, gH = _c(grad_m), _c(grad_H)
-    ws = torch.empty(4 * L * M * M, dtype=F64, device=H.device)
+    ws = torch.empty(4 * L * M * M if M > 64 else 1, dtype=F64, device=H.device)
     info = torch.zeros(4, dtype=torch.int32, device=H.device)
+    hi = _c(Hinv) if Hinv is not None else None
     with torch.cuda.device(H.device):
-        rc = lib.lvae_ng_step_f64(ptr(m2), ptr(H2), ptr(gm), ptr(gH), float(lr), L, M, ptr(ws), ptr(info),
+        rc = lib.lvae_ng_step_f64(ptr(m2), ptr(H2), ptr(gm), ptr(gH), ptr(hi), float(lr), L, M, ptr(ws), ptr(info),
                                   stream_ptr(H.device))
     check(rc, "lvae_ng_step_f64")
     return m2.view_as(m), H2, info
