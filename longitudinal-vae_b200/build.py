@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "liblvae_b200.so")
-SOURCES = ["lvae_dense.cu", "lvae_kld.cu", "lvae_kld64.cu", "lvae_prep.cu", "lvae_subjects_fused.cu"]
+SOURCES = ["lvae_dense.cu", "lvae_kld.cu", "lvae_kld64.cu", "lvae_prep.cu", "lvae_subjects_fused.cu", "lvae_subjects_fused2.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-shared"]
 

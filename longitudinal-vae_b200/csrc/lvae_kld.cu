@@ -47,8 +47,19 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.T3 = o; o += L * MM;
     w.a = o; o += L * M;
     w.logdet = o; o += L * 2;
-    w.Bi = o; o += L * p->sum_T2;
+    w.v2 = (p->path == 0 || p->path == 2) && lvae_fused2_supported(p) ? 1 : 0;
+    w.TP = (p->T_max + 3) & ~3;
+    if (w.TP < 4) w.TP = 4;
+    w.gstride = (p->P_b + w.nchunk - 1) / w.nchunk + 1;
+    w.Bi = o; o += w.v2 ? 0 : L * p->sum_T2;
     w.off2 = o; o += (int64_t)p->P_b + 1;
+    o += o & 1;
+    w.Lrows = o; o += w.v2 ? L * (int64_t)p->N_b * w.TP : 0;
+    w.bmu = o; o += w.v2 ? L * (int64_t)p->N_b : 0;
+    o += o & 1;
+    w.gtab = o; o += w.v2 ? ((int64_t)w.nchunk * w.gstride * LVAE_F2_GT + 1) / 2 : 0;
+    o += o & 1;
+    w.gcount = o; o += w.v2 ? (w.nchunk + 1) / 2 : 0;
     w.part = o; o += (int64_t)w.nchunk * L * w.stride;   // subject partials (S, ng1, da, A, hyp)
     w.ppart = o; o += (int64_t)w.nprep * L * (LVAE_NSCAL + w.nh);   // prep partials (scalars, hyp)
     w.total = o;
@@ -582,7 +593,8 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
     w.Bi_stride = p->sum_T2;
     const double c = 0.5 * p->scale;
     if (p->P_b > 0) {
-        rc = lvae_block_offsets(p->offsets, p->P_b, reinterpret_cast<int64_t*>(p->workspace + w.off2), st);
+        if (w.v2) rc = lvae_plan_groups_launch(p, w, st);
+        else rc = lvae_block_offsets(p->offsets, p->P_b, reinterpret_cast<int64_t*>(p->workspace + w.off2), st);
         if (rc) return rc;
         const int Tm = p->T_max > 0 ? p->T_max : 1;
         const size_t s1 = prep_smem(sp, Tm, p->Q);
@@ -603,10 +615,10 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             LVAE_COUNT_LAUNCH();
         }
         lvae_prof_end(1, st);
-        bool fused = (p->path == 2) || (p->path == 0 && lvae_fused_supported(p));
+        bool fused = w.v2 || (p->path == 2) || (p->path == 3) || (p->path == 0 && lvae_fused_supported(p));
         if (fused) {
             lvae_prof_begin(2, st);
-            rc = lvae_subjects_fused_launch(p, sp, w, st);
+            rc = w.v2 ? lvae_subjects_fused2_launch(p, sp, w, st) : lvae_subjects_fused_launch(p, sp, w, st);
             lvae_prof_end(2, st);
             if (rc) return rc;
         } else {

@@ -2,6 +2,9 @@
 #pragma once
 #include "lvae_host.h"
 
+#define LVAE_F2_ROWS 24
+#define LVAE_F2_GT 8
+
 struct KldLayout {
     int64_t Ki, Hi, G, W, T1, T2, T3;   // [L, M*M] each
     int64_t a;                          // [L, M]
@@ -13,6 +16,12 @@ struct KldLayout {
     int64_t ppart;                      // [nchunk, L, NSCAL+nh] per-CTA partials of the prep pass
     int64_t total;
     int64_t stride;                     // statistics row length
+    // second-generation fused pass (lvae_subjects_fused2.cu)
+    int64_t Lrows;                      // [L, N_b, TP]  rows of the per-subject L^-1 (lower triangular, zero padded)
+    int64_t bmu;                        // [L, N_b]      B_p^-1 mu_p
+    int64_t gtab;                       // int32 [nchunk, gstride, LVAE_F2_GT] row-group plan
+    int64_t gcount;                     // int32 [nchunk]
+    int TP, gstride, v2;
     int nh, nchunk;                     // nchunk: CTAs per latent of the subject pass
     int nprep;                          // partial rows per latent of the prep pass
 };
@@ -31,3 +40,8 @@ int lvae_head64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const Kld
 int lvae_tail64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
 int lvae_ng64_launch(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hi, double lr, int L,
                      int M, int32_t* info, cudaStream_t st);
+
+// second-generation fused subject pass (two 8-warp sets per CTA, SYRK, cp.async prefetch)
+bool lvae_fused2_supported(const lvae_kld_problem_t* p);
+int lvae_plan_groups_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);
+int lvae_subjects_fused2_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);

@@ -67,8 +67,10 @@ __device__ __forceinline__ void warp_mm(const double* __restrict__ A, const doub
 }
 
 __global__ void __launch_bounds__(PWMAX * 32)
-k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int Tmax, int ld,
-            const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ log_v,
+k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int N_b, int Tmax,
+            int ld,
+            const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ mu,
+            const double* __restrict__ log_v,
             const double* __restrict__ ls, const double* __restrict__ os, const double* __restrict__ noise, double c,
             double* __restrict__ d_log_v, double* __restrict__ ws, int32_t* info) {
     extern __shared__ double sm[];
@@ -82,14 +84,15 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
     load_exp_table(etab);
     const int TP8 = (Tmax + 7) & ~7;
     const int asz = TP8 * ld;
-    double* A1 = sm + (size_t)wid * (3 * asz + Tmax * Q + Tmax);
+    double* A1 = sm + (size_t)wid * (3 * asz + Tmax * Q + 2 * Tmax);
     double* A2 = A1 + asz;
     double* A3 = A2 + asz;
     double* xs = A3 + asz;
     double* ev = xs + Tmax * Q;
+    double* mw = ev + Tmax;
     for (int e = lane; e < 3 * asz; e += 32) A1[e] = 0.0;
     __syncthreads();
-    const int64_t* off2 = reinterpret_cast<const int64_t*>(ws + w.off2);
+    const int64_t* off2 = reinterpret_cast<const int64_t*>(ws + w.off2);   // (block layout only; unused when w.v2)
 
     double sC = 0.0, sD1 = 0.0, sBt = 0.0, sF = 0.0, gno = 0.0;
     double gos[NCMAX], gls[NCMAX];
@@ -112,6 +115,7 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
             const double lv = log_v[(size_t)(r0 + t) * L + l];
             ev[t] = exp(lv);
             sF += lv;
+            if (w.v2) mw[t] = mu[(size_t)(r0 + t) * L + l];
         }
         __syncwarp();
         // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) -------------------------------------------------
@@ -154,6 +158,13 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
             }
         }
         __syncwarp();
+        if (w.v2) {   // rows of L^-1 for the fused pass: [row][k'], k' = column inside the subject, zero padded to TP
+            double* gl = ws + w.Lrows + ((size_t)l * N_b + r0) * w.TP;
+            for (int e = lane; e < T * w.TP; e += 32) {
+                const int i = e / w.TP, k = e % w.TP;
+                gl[e] = (k <= i) ? A2[i * ld + k] : 0.0;
+            }
+        }
         // ---- B^-1 = L^-T L^-1 into A3 --------------------------------------------------------------------------------
         warp_mm<true, true>(A2, A2, A3, T, ld, nt8, nk4, g, q);
         __syncwarp();
@@ -184,7 +195,15 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
         warp_mm<false, false>(A3, A2, A1, T, ld, nt8, nk4, g, q);
         __syncwarp();
         // ---- B^-1 out ; local adjoint of B_p: (B^-1 - X2) [times c at the end] ; K1 hyper-gradients ; Bt ; d_log_v -------
-        {
+        if (w.v2) {
+            // rows of L^-1 (kept in A2 until X1 overwrote it: re-derive is not possible, so they were exported before X1)
+            double* gb = ws + w.bmu + (size_t)l * N_b + r0;
+            for (int t = lane; t < T; t += 32) {
+                double s = 0.0;
+                for (int k = 0; k < T; ++k) s += A3[t * ld + k] * mw[k];
+                gb[t] = s;
+            }
+        } else {
             double* gBi = ws + w.Bi + (size_t)l * w.Bi_stride + off2[p];
             int i = 0, j = lane;
             while (j >= T) { j -= T; ++i; }
@@ -249,7 +268,7 @@ static int ld_for(int Tmax) {
 
 static size_t warp_doubles(int Tm, int Q) {
     const int ld = ld_for(Tm), TP8 = (Tm + 7) & ~7;
-    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + Tm;
+    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + 2 * Tm;
 }
 
 static int warps_per_cta(int Tm, int Q) {
@@ -288,8 +307,8 @@ int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const 
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         attr = smem;
     }
-    k_prep_warp<<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, Tm, ld, p->x, p->offsets,
-                                                                p->log_v, p->lengthscale, p->outputscale, p->noise,
+    k_prep_warp<<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, Tm, ld, p->x, p->offsets,
+                                                                p->mu, p->log_v, p->lengthscale, p->outputscale, p->noise,
                                                                 0.5 * p->scale, p->d_log_v, p->workspace, p->info);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());

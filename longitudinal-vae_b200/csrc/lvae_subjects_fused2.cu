@@ -1,0 +1,550 @@
+// Fused per-subject pass, second generation (M <= 64, at most 24 rows per subject): sm_100a, FP64 tensor pipe (DMMA.8x8x4).
+//
+// One CTA owns a latent l and a contiguous range of subjects and runs TWO independent 8-warp sets.  The sets share W,
+// a = Kzz^-1 m, Z_l and the hyper-parameters in shared memory, each works on its own row groups (whole subjects, <= 24
+// rows) with named barriers, so one set's latency-bound intervals overlap the other's tensor-pipe intervals.
+// Per group (set-local barrier between intervals):
+//   J0  wait for the cp.async prefetch of this group (covariates, mu, B^-1 mu, block-diagonal L^-1) ; issue the next one
+//   J1  Kxz (R x 64) from covariates in registers ; f_c stay in registers ; partial dots of r = Kxz a - mu
+//   J2  U = L^-1 Kxz            (DMMA, lower-triangular k-range)
+//   J3  V = L^-T U              (DMMA, upper-triangular k-range) ; S += U^T U (SYRK: 36 lower tiles, accumulators in
+//       registers for the whole kernel) ; ng1 += V^T mu ; partial dots of u = V a - B^-1 mu
+//   J4  Y = V W                 (DMMA, accumulators stay in registers)
+//   J5  adjoint of Kxz = 2c u a^T + 2Y contracted with d k_c / d theta (f_c from registers) ; da ; A ; d_mu ; Y -> smem
+//   J6  Q = Y V^T on the subject-diagonal upper tiles (DMMA) ; adjoint of B_p = -(c u u^T + Q) contracted with d K1
+// Row groups are planned once per step by k_plan_groups (they do not depend on the latent).  L^-1 and B^-1 mu come
+// from the prep kernel in row-major per-row layout.  Nothing of size T x M touches HBM.
+#include "lvae_kld.h"
+
+namespace {
+
+constexpr int RG = LVAE_F2_ROWS;   // 24 rows per group
+constexpr int NMT = RG / 8;        // 3 m-tiles
+constexpr int LD = 68;
+constexpr int LDL = 28;
+constexpr int SETW = 8;            // warps per set
+constexpr int GT = LVAE_F2_GT;     // ints per group-table entry
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 8-byte asynchronous copy; !valid writes zeros (src-size 0) and never forms an out-of-range address (falls back to `safe`)
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid, const void* safe) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 8 : 0;
+    const void* src = valid ? gmem : safe;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void set_barrier(int set) {
+    asm volatile("bar.sync %0, %1;" ::"r"(set + 1), "r"(SETW * 32) : "memory");
+}
+__device__ __forceinline__ void tri2(int e, int& i, int& j) {   // e-th element of a lower triangle, j <= i
+    i = 0;
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    j = e - i * (i + 1) / 2;
+}
+
+struct SetSmem {
+    double* B1;      // [RG][LD]  Kxz, then V
+    double* B2;      // [RG][LD]  U, then Y
+    double* Lg;      // [2][RG][LDL]
+    double* xs;      // [2][RG][Q]
+    double* mus;     // [2][RG]
+    double* bmu;     // [2][RG]
+    double* rpart;   // [SETW][RG]
+    double* upart;   // [SETW][RG]
+    double* rs;      // [RG]
+    double* us;      // [RG]
+    int* meta;       // [3][GT]
+    int* blo;        // [RG]
+    int* bhi;        // [RG]
+};
+
+__host__ __device__ inline size_t set_doubles(int Q) {
+    return 2 * (size_t)RG * LD + 2 * (size_t)RG * LDL + 2 * (size_t)RG * Q + 4 * RG + 2 * SETW * RG + 2 * RG +
+           (3 * GT + 2 * RG + 1) / 2 + 2;
+}
+__host__ __device__ inline size_t fused2_doubles(int Q, int nh) {
+    return (size_t)64 * LD + (size_t)64 * Q + 64 + (size_t)16 * (nh + 1) + 2 * 16 * 8 + 36 * 64 + 2 * set_doubles(Q);
+}
+
+template <int NC0, int NC1>
+__global__ void __launch_bounds__(512, 1)
+k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b, int TP,
+                  const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ z,
+                  const double* __restrict__ ls, const double* __restrict__ os, double c, double* __restrict__ d_mu,
+                  double* __restrict__ ws) {
+    extern __shared__ double sm[];
+    __shared__ double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
+    const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
+    const int set = tid >> 8, lt = tid & 255, wid = tid >> 5, wl = wid & 7, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int nh = hyp_count(sp), MM = M * M;
+
+    double* p = sm;
+    double* const Wp = p; p += 64 * LD;
+    double* const zs = p; p += 64 * Q;
+    double* const av = p; p += 64;
+    double* const hyp = p; p += 16 * (nh + 1);
+    double* const cols = p; p += 2 * 16 * 8;
+    double* const sxch = p; p += 36 * 64;           // S exchange between the two sets at the end
+    p += (size_t)set * set_doubles(Q);
+    SetSmem S;
+    S.B1 = p; p += RG * LD;
+    S.B2 = p; p += RG * LD;
+    S.Lg = p; p += 2 * RG * LDL;
+    S.xs = p; p += 2 * RG * Q;
+    S.mus = p; p += 2 * RG;
+    S.bmu = p; p += 2 * RG;
+    S.rpart = p; p += SETW * RG;
+    S.upart = p; p += SETW * RG;
+    S.rs = p; p += RG;
+    S.us = p; p += RG;
+    S.meta = reinterpret_cast<int*>(p);             // 16-byte aligned: every preceding block is an even count of doubles
+    S.blo = S.meta + 3 * GT;
+    S.bhi = S.blo + RG;
+
+    // ---- per-CTA constants -------------------------------------------------------------------------------------------
+    if (tid < sp.n_ls) { const double v = ls[(size_t)tid * L + l]; hil2[tid] = 0.5 / (v * v); il3[tid] = 1.0 / (v * v * v); }
+    if (tid < sp.n0 + sp.n1) osc[tid] = os[(size_t)tid * L + l];
+    load_exp_table(etab);
+    {
+        const double* Wl = ws + w.W + (size_t)l * MM;
+        for (int e = tid; e < 64 * LD; e += 512) {
+            const int i = e / LD, j = e % LD;
+            Wp[e] = (i < M && j < M) ? Wl[i * M + j] : 0.0;
+        }
+        for (int e = tid; e < 64 * Q; e += 512) zs[e] = (e < M * Q) ? z[(size_t)l * M * Q + e] : 0.0;
+        if (tid < 64) av[tid] = tid < M ? ws[w.a + (size_t)l * M + tid] : 0.0;
+        for (int e = tid; e < 16 * (nh + 1); e += 512) hyp[e] = 0.0;
+    }
+    const int* gtab = reinterpret_cast<const int*>(ws + w.gtab) + (size_t)chunk * w.gstride * GT;
+    const int ngroups = reinterpret_cast<const int*>(ws + w.gcount)[chunk];
+    const double* Lrows = ws + w.Lrows + (size_t)l * N_b * TP;
+    const double* bmu_g = ws + w.bmu + (size_t)l * N_b;
+
+    // this thread's Kxz / U / V / Y elements: rows 8*mt + g (mt = 0..2), columns 8*wl + 2q + {0,1}
+    const int j0 = 8 * wl + 2 * q;
+    // SYRK tiles of S owned by this warp (lower triangle of the 8 x 8 tile grid, 36 tiles over 8 warps)
+    int sti[5], stj[5];
+    double sacc[5][2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int e = wl + 8 * i;
+        if (e < 36) tri2(e, sti[i], stj[i]); else { sti[i] = -1; stj[i] = 0; }
+        sacc[i][0] = sacc[i][1] = 0.0;
+    }
+    double ng1acc[2] = {0.0, 0.0}, daacc[2] = {0.0, 0.0}, accA = 0.0;
+    double gos[NC0], gls[NC0], g1os[NC1], g1ls[NC1], gno = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < NC0; ++cc) gos[cc] = gls[cc] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NC1; ++k) g1os[k] = g1ls[k] = 0.0;
+
+    // issue the prefetch of group `gi` (its meta entry must already be visible in smem slot `slot`) into data buffer `buf`
+    auto issue_data = [&](int slot, int buf) {
+        const int* mt_ = S.meta + slot * GT;
+        const int row0 = mt_[0], R = mt_[1];
+        for (int e = lt; e < RG * Q; e += 256) cp_async8(S.xs + buf * RG * Q + e, x + (size_t)row0 * Q + e, e < R * Q, x);
+        if (lt < RG) {
+            cp_async8(S.mus + buf * RG + lt, mu + (size_t)(row0 + lt) * L + l, lt < R, x);
+            cp_async8(S.bmu + buf * RG + lt, bmu_g + row0 + lt, lt < R, x);
+        }
+        for (int e = lt; e < RG * RG; e += 256) {
+            const int t = e / RG, k = e % RG;
+            int lo = 0, hi = 0;
+            if (t < R) {
+#pragma unroll
+                for (int s = 0; s < 5; ++s) {
+                    const int end = mt_[3 + s];
+                    if (t >= end) lo = end;
+                }
+#pragma unroll
+                for (int s = 4; s >= 0; --s) {
+                    const int end = mt_[3 + s];
+                    if (t < end) hi = end;
+                }
+            }
+            const bool valid = (k >= lo) && (k < hi);
+            cp_async8(S.Lg + buf * RG * LDL + t * LDL + k, Lrows + (size_t)(row0 + t) * TP + (k - lo), valid, x);
+        }
+    };
+    auto issue_meta = [&](int gi, int slot) {
+        if (lt < 2) cp_async16(S.meta + slot * GT + 4 * lt, gtab + (size_t)gi * GT + 4 * lt);
+    };
+
+    __syncthreads();
+    // ---- prologue of the 3-stage prefetch pipeline -------------------------------------------------------------------------
+    const int first = set;
+    if (first < ngroups) {
+        issue_meta(first, 0);
+        if (first + 2 < ngroups) issue_meta(first + 2, 1);
+        cp_async_commit();
+        cp_async_wait_all();
+        set_barrier(set);
+        issue_data(0, 0);
+        cp_async_commit();
+    }
+
+    int it = 0;
+    for (int gi = first; gi < ngroups; gi += 2, ++it) {
+        const int buf = it & 1, slot = it % 3;
+        // ---- J0 ----------------------------------------------------------------------------------------------------------
+        cp_async_wait_all();
+        set_barrier(set);
+        const int* mt_ = S.meta + slot * GT;
+        const int row0 = mt_[0], R = mt_[1];
+        const int R8 = (R + 7) & ~7, nmt = R8 >> 3, nk4 = (R + 3) >> 2;
+        const double* xs = S.xs + buf * RG * Q;
+        const double* mus = S.mus + buf * RG;
+        const double* Lg = S.Lg + buf * RG * LDL;
+        if (lt < RG) {
+            int lo = lt, hi = lt;
+            if (lt < R) {
+                lo = 0; hi = 0;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) { const int end = mt_[3 + s]; if (lt >= end) lo = end; }
+#pragma unroll
+                for (int s = 4; s >= 0; --s) { const int end = mt_[3 + s]; if (lt < end) hi = end; }
+            }
+            S.blo[lt] = lo; S.bhi[lt] = hi;
+        }
+        if (gi + 2 < ngroups) {
+            issue_data((it + 1) % 3, buf ^ 1);
+            if (gi + 4 < ngroups) issue_meta(gi + 4, (it + 2) % 3);
+            cp_async_commit();
+        }
+
+        // ---- J1: Kxz from covariates ; f_c in registers ; partial dots of r --------------------------------------------------
+        double fc[NMT][2][NC0];
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            double kx[2] = {0.0, 0.0};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = j0 + e;
+                const bool valid = (t < R) && (j < M);
+#pragma unroll
+                for (int cc = 0; cc < NC0; ++cc) {
+                    double d2, f = 0.0;
+                    if (valid) f = comp_value(sp, cc, xs + t * Q, zs + j * Q, hil2, d2, etab);
+                    fc[mt][e][cc] = f;
+                    kx[e] += osc[cc] * f;
+                }
+            }
+            *reinterpret_cast<double2*>(S.B1 + t * LD + j0) = make_double2(kx[0], kx[1]);
+            double pr = kx[0] * av[j0] + kx[1] * av[j0 + 1];
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+            if (q == 0) S.rpart[wl * RG + t] = pr;
+        }
+        set_barrier(set);
+
+        // ---- J2: U = L^-1 Kxz (rows of a tile only see k <= row, inside their subject) ; r -----------------------------------------
+        if (lt < RG) {
+            double s = -mus[lt];
+#pragma unroll
+            for (int ww = 0; ww < SETW; ++ww) s += S.rpart[ww * RG + lt];
+            S.rs[lt] = s;
+        }
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            double u0 = 0.0, u1 = 0.0;
+            if (mt < nmt) {
+                const int klo = S.blo[8 * mt] >> 2;
+                const int khi = min(2 * mt + 2, (S.bhi[min(8 * mt + 7, R - 1)] + 3) >> 2);
+                for (int ks = klo; ks < khi; ++ks)
+                    dmma(u0, u1, Lg[t * LDL + 4 * ks + q], S.B1[(4 * ks + q) * LD + 8 * wl + g]);
+            }
+            *reinterpret_cast<double2*>(S.B2 + t * LD + j0) = make_double2(u0, u1);
+        }
+        set_barrier(set);
+
+        // ---- J3: V = L^-T U -> B1 ; ng1 ; partial dots of u ; S += U^T U ------------------------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            double v0 = 0.0, v1 = 0.0;
+            if (mt < nmt) {
+                const int khi = (S.bhi[min(8 * mt + 7, R - 1)] + 3) >> 2;
+                for (int ks = 2 * mt; ks < khi; ++ks)
+                    dmma(v0, v1, Lg[(4 * ks + q) * LDL + 8 * mt + g], S.B2[(4 * ks + q) * LD + 8 * wl + g]);
+            }
+            *reinterpret_cast<double2*>(S.B1 + t * LD + j0) = make_double2(v0, v1);
+            const double mt_mu = mus[t];
+            ng1acc[0] += v0 * mt_mu;
+            ng1acc[1] += v1 * mt_mu;
+            double pu = v0 * av[j0] + v1 * av[j0 + 1];
+            pu += __shfl_xor_sync(0xffffffffu, pu, 1);
+            pu += __shfl_xor_sync(0xffffffffu, pu, 2);
+            if (q == 0) S.upart[wl * RG + t] = pu;
+        }
+        for (int ks = 0; ks < nk4; ++ks) {
+            const double* Urow = S.B2 + (4 * ks + q) * LD + g;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (sti[i] >= 0) dmma(sacc[i][0], sacc[i][1], Urow[8 * sti[i]], Urow[8 * stj[i]]);
+            }
+        }
+        set_barrier(set);
+
+        // ---- J4: u = V a - B^-1 mu ; Y = V W ---------------------------------------------------------------------------------
+        if (lt < RG) {
+            double s = -S.bmu[buf * RG + lt];
+#pragma unroll
+            for (int ww = 0; ww < SETW; ++ww) s += S.upart[ww * RG + lt];
+            S.us[lt] = lt < R ? s : 0.0;
+        }
+        double yacc[NMT][2];
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) yacc[mt][0] = yacc[mt][1] = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+            const double b_ = Wp[(4 * ks + q) * LD + 8 * wl + g];
+#pragma unroll
+            for (int mt = 0; mt < NMT; ++mt) {
+                if (mt < nmt) dmma(yacc[mt][0], yacc[mt][1], S.B1[(8 * mt + g) * LD + 4 * ks + q], b_);
+            }
+        }
+        set_barrier(set);
+
+        // ---- J5: adjoint of Kxz against the component derivatives ; da ; A ; d_mu ; Y -> B2 ------------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            const double ut = S.us[t];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = j0 + e;
+                const double gbar = 2.0 * c * ut * av[j] + 2.0 * yacc[mt][e];
+                double kx = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < NC0; ++cc) {
+                    const double f = fc[mt][e][cc];
+                    kx += osc[cc] * f;
+                    gos[cc] += gbar * f;
+                    const int rd = sp.rbf_dim[cc];
+                    if (rd >= 0) {
+                        const double d = xs[t * Q + rd] - zs[j * Q + rd];
+                        gls[cc] += gbar * f * (d * d);
+                    }
+                }
+                daacc[e] += kx * ut;
+            }
+            *reinterpret_cast<double2*>(S.B2 + t * LD + j0) = make_double2(yacc[mt][0], yacc[mt][1]);
+        }
+        if (lt < R) {
+            accA += S.rs[lt] * S.us[lt];
+            d_mu[(size_t)(row0 + lt) * L + l] = -2.0 * c * S.us[lt];
+        }
+        set_barrier(set);
+
+        // ---- J6: Q = Y V^T on subject-diagonal upper tiles ; adjoint of B_p against d K1 / d theta -----------------------------------
+        if (wl < 6) {
+            int jt, i;
+            tri2(wl, jt, i);                                 // i <= jt
+            if (jt < nmt && 8 * jt < S.bhi[min(8 * i + 7, R - 1)]) {
+                double q0 = 0.0, q1 = 0.0;
+                const double* Ya = S.B2 + (8 * i + g) * LD + q;
+                const double* Vb = S.B1 + (8 * jt + g) * LD + q;
+#pragma unroll 4
+                for (int ks = 0; ks < 16; ++ks) dmma(q0, q1, Ya[4 * ks], Vb[4 * ks]);
+                const int t = 8 * i + g;
+                const double wgt = jt > i ? 2.0 : 1.0;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int t2 = 8 * jt + 2 * q + e;
+                    if (t < R && t2 < R && S.blo[t] == S.blo[t2]) {
+                        const double gB = -wgt * (c * S.us[t] * S.us[t2] + (e ? q1 : q0));
+                        if (t == t2) gno += gB;
+#pragma unroll
+                        for (int k = 0; k < NC1; ++k) {
+                            const int cc = sp.n0 + k;
+                            double d2;
+                            const double f = comp_value(sp, cc, xs + t * Q, xs + t2 * Q, hil2, d2, etab);
+                            g1os[k] += gB * f;
+                            if (sp.rbf_dim[cc] >= 0) g1ls[k] += gB * f * d2;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- CTA epilogue: per-thread accumulators -> fixed-order partials of this CTA ------------------------------------------------------
+    double* part = ws + w.part + ((size_t)chunk * L + l) * w.stride;
+    {
+        const double a_ = warp_sum(accA);
+        if (lane == 0) hyp[wid * (nh + 1)] = a_;
+#pragma unroll
+        for (int cc = 0; cc < NC0; ++cc) {
+            const double s1 = warp_sum(gos[cc]);
+            const double s2 = warp_sum(gls[cc]);
+            if (lane == 0) {
+                hyp[wid * (nh + 1) + 1 + sp.n_ls + cc] += s1;
+                if (sp.rbf_dim[cc] >= 0) hyp[wid * (nh + 1) + 1 + sp.ls_idx[cc]] += s2 * osc[cc] * il3[sp.ls_idx[cc]];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NC1; ++k) {
+            const int cc = sp.n0 + k;
+            const double s1 = warp_sum(g1os[k]);
+            const double s2 = warp_sum(g1ls[k]);
+            if (lane == 0) {
+                hyp[wid * (nh + 1) + 1 + sp.n_ls + cc] += s1;
+                if (sp.rbf_dim[cc] >= 0) hyp[wid * (nh + 1) + 1 + sp.ls_idx[cc]] += s2 * osc[cc] * il3[sp.ls_idx[cc]];
+            }
+        }
+        const double n_ = warp_sum(gno);
+        if (lane == 0) hyp[wid * (nh + 1) + nh] += n_;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double a2 = ng1acc[e], b2 = daacc[e];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) { a2 += __shfl_xor_sync(0xffffffffu, a2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+            if (g == 0) { cols[(0 * 16 + wid) * 8 + 2 * q + e] = a2; cols[(1 * 16 + wid) * 8 + 2 * q + e] = b2; }
+        }
+        if (set == 1) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (sti[i] >= 0) {
+                    double* d = sxch + (wl + 8 * i) * 64 + g * 8 + 2 * q;
+                    d[0] = sacc[i][0]; d[1] = sacc[i][1];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (set == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (sti[i] >= 0) {
+                const double* d = sxch + (wl + 8 * i) * 64 + g * 8 + 2 * q;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int ii = 8 * sti[i] + g, jj = 8 * stj[i] + 2 * q + e;
+                    if (ii < M && jj < M) {
+                        const double v = sacc[i][e] + d[e];
+                        part[stats_off_S() + (size_t)ii * M + jj] = v;
+                        if (sti[i] != stj[i]) part[stats_off_S() + (size_t)jj * M + ii] = v;
+                    }
+                }
+            }
+        }
+    }
+    if (tid < 64 && tid < M) {
+        const int ntile = tid >> 3, cidx = tid & 7;
+        part[stats_off_ng1(M) + tid] = cols[(0 * 16 + ntile) * 8 + cidx] + cols[(0 * 16 + ntile + 8) * 8 + cidx];
+        part[stats_off_da(M) + tid] = cols[(1 * 16 + ntile) * 8 + cidx] + cols[(1 * 16 + ntile + 8) * 8 + cidx];
+    }
+    if (tid <= nh) {
+        double s = 0.0;
+        for (int ww = 0; ww < 16; ++ww) s += hyp[ww * (nh + 1) + tid];
+        if (tid == 0) {
+            for (int k = 0; k < LVAE_NSCAL; ++k) part[stats_off_scal(M) + k] = 0.0;
+            part[stats_off_scal(M) + SC_A] = s;
+        } else {
+            part[stats_off_hyp(M) + tid - 1] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// group planning: one CTA per chunk; greedy packing of whole subjects into groups of <= RG rows and <= 5 subjects
+// entry: row0, R, nsub, end_1..end_5 (local row offsets where each subject ends; unused = R)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_plan_groups(const int32_t* __restrict__ offsets, int P_b, int per, int gstride,
+                                                     int* __restrict__ gtab, int* __restrict__ gcount) {
+    __shared__ int offs[1025];
+    const int chunk = blockIdx.x, tid = threadIdx.x;
+    const int p_begin = min(P_b, chunk * per), p_end = min(P_b, p_begin + per);
+    int* tab = gtab + (size_t)chunk * gstride * GT;
+    int ng = 0;
+    int cur_row0 = 0, cur_rows = 0, cur_n = 0, ends[5];
+    for (int base = p_begin; base < p_end; base += 1024) {
+        const int n = min(1024, p_end - base);
+        __syncthreads();
+        for (int i = tid; i <= n; i += 256) offs[i] = offsets[base + i];
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < n; ++i) {
+                const int T = offs[i + 1] - offs[i];
+                if (cur_n > 0 && (cur_rows + T > RG || cur_n == 5)) {
+                    int* e = tab + (size_t)ng * GT;
+                    e[0] = cur_row0; e[1] = cur_rows; e[2] = cur_n;
+                    for (int s = 0; s < 5; ++s) e[3 + s] = s < cur_n ? ends[s] : cur_rows;
+                    ++ng;
+                    cur_n = 0; cur_rows = 0;
+                }
+                if (cur_n == 0) cur_row0 = offs[i];
+                cur_rows += T;
+                ends[cur_n++] = cur_rows;
+            }
+        }
+    }
+    if (tid == 0) {
+        if (cur_n > 0) {
+            int* e = tab + (size_t)ng * GT;
+            e[0] = cur_row0; e[1] = cur_rows; e[2] = cur_n;
+            for (int s = 0; s < 5; ++s) e[3 + s] = s < cur_n ? ends[s] : cur_rows;
+            ++ng;
+        }
+        gcount[chunk] = ng;
+    }
+}
+
+template <int NC0, int NC1>
+int launch2(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    const size_t smem = sizeof(double) * fused2_doubles(p->Q, w.nh);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_subjects_fused2<NC0, NC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return lvae_cuda_rc(e);
+        attr = smem;
+    }
+    k_subjects_fused2<NC0, NC1><<<dim3(w.nchunk, p->L), 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, w.TP, p->x, p->mu,
+                                                                        p->z, p->lengthscale, p->outputscale,
+                                                                        0.5 * p->scale, p->d_mu, p->workspace);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+}  // namespace
+
+bool lvae_fused2_supported(const lvae_kld_problem_t* p) {
+    return p->M <= 64 && p->T_max <= RG && p->ks.n_comp0 >= 1 && p->ks.n_comp0 <= 4 && p->ks.n_comp1 >= 1 &&
+           p->ks.n_comp1 <= 2 && p->Q <= 10;
+}
+
+int lvae_plan_groups_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st) {
+    const int per = (p->P_b + w.nchunk - 1) / w.nchunk;
+    k_plan_groups<<<w.nchunk, 256, 0, st>>>(p->offsets, p->P_b, per, w.gstride,
+                                            reinterpret_cast<int*>(p->workspace + w.gtab),
+                                            reinterpret_cast<int*>(p->workspace + w.gcount));
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+int lvae_subjects_fused2_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    if (!lvae_fused2_supported(p)) return LVAE_E_TOO_LARGE;
+    const int key = sp.n0 * 10 + sp.n1;
+    switch (key) {
+        case 11: return launch2<1, 1>(p, sp, w, st);
+        case 12: return launch2<1, 2>(p, sp, w, st);
+        case 21: return launch2<2, 1>(p, sp, w, st);
+        case 22: return launch2<2, 2>(p, sp, w, st);
+        case 31: return launch2<3, 1>(p, sp, w, st);
+        case 32: return launch2<3, 2>(p, sp, w, st);
+        case 41: return launch2<4, 1>(p, sp, w, st);
+        case 42: return launch2<4, 2>(p, sp, w, st);
+    }
+    return LVAE_E_BADARG;
+}
