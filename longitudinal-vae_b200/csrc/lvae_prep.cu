@@ -31,6 +31,109 @@ __device__ __forceinline__ void tri_index(int e, int& i, int& j) {
     j = e - i * (i + 1) / 2;
 }
 
+// advance (i, j) of a lower-triangle element by 32 positions (row-major, j <= i)
+__device__ __forceinline__ void tri_step32(int& i, int& j) {
+    j += 32;
+    while (j > i) { j -= i + 1; ++i; }
+}
+
+// Warp-level blocked Cholesky of the T x T matrix A (row stride ld, zero padded), 8 x 8 blocks: the diagonal block is
+// factored column by column, the panel below by one lane per row (forward substitution), the trailing matrix by DMMA.
+// dinv[k] receives 1 / L_kk.  Returns 0 or 1 + first non-positive pivot (warp-uniform).
+__device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int ld, double* __restrict__ dinv, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const int nb = (T + 7) >> 3;
+    int bad = 0;
+    for (int kb = 0; kb < nb; ++kb) {
+        const int k0 = 8 * kb, bs = min(8, T - k0);
+        for (int k = 0; k < bs; ++k) {
+            const double akk = A[(k0 + k) * ld + k0 + k];
+            if (!(akk > 0.0) && bad == 0) bad = k0 + k + 1;
+            const double ri = rsqrt(akk);
+            __syncwarp();
+            if (lane == k) { A[(k0 + k) * ld + k0 + k] = akk * ri; dinv[k0 + k] = ri; }
+            if (lane > k && lane < bs) A[(k0 + lane) * ld + k0 + k] *= ri;
+            __syncwarp();
+            if (lane < 28) {
+                int r = 0;
+                while ((r + 1) * (r + 2) / 2 <= lane) ++r;
+                const int c_ = lane - r * (r + 1) / 2 + 1;
+                r += 1;
+                if (c_ > k && r < bs) A[(k0 + r) * ld + k0 + c_] -= A[(k0 + r) * ld + k0 + k] * A[(k0 + c_) * ld + k0 + k];
+            }
+            __syncwarp();
+        }
+        if (kb + 1 < nb) {
+            for (int r = k0 + 8 + lane; r < T; r += 32) {           // panel rows: x D^T = a
+                double xr[8];
+#pragma unroll
+                for (int c_ = 0; c_ < 8; ++c_) {
+                    double s = A[r * ld + k0 + c_];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < c_) s -= xr[k] * A[(k0 + c_) * ld + k0 + k];
+                    xr[c_] = s * dinv[k0 + c_];
+                }
+#pragma unroll
+                for (int c_ = 0; c_ < 8; ++c_) A[r * ld + k0 + c_] = xr[c_];
+            }
+            __syncwarp();
+            for (int ti = kb + 1; ti < nb; ++ti) {                   // trailing update on the lower tiles
+                for (int tj = kb + 1; tj <= ti; ++tj) {
+                    const int i = 8 * ti + g, j = 8 * tj + 2 * q;
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        dmma(c0, c1, A[i * ld + k0 + 4 * ks + q], A[(8 * tj + g) * ld + k0 + 4 * ks + q]);
+                    if (i < T && j < T) A[i * ld + j] -= c0;
+                    if (i < T && j + 1 < T) A[i * ld + j + 1] -= c1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    return bad;
+}
+
+// X = L^-1 (lower, T x T) into a zero-initialised X: 8 x 8 diagonal blocks by one lane per column, then the block
+// sub-diagonals X_ij = -X_ii (sum_k L_ik X_kj) on the tensor pipe.  tile: 64 doubles of per-warp scratch.
+__device__ __forceinline__ void warp_tri_inverse(const double* __restrict__ Lc, double* __restrict__ X, int T, int ld,
+                                                 const double* __restrict__ dinv, double* __restrict__ tile, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const int nb = (T + 7) >> 3;
+    for (int j = lane; j < T; j += 32) {
+        const int kend = min(T, (j & ~7) + 8);
+        X[j * ld + j] = dinv[j];
+        for (int i = j + 1; i < kend; ++i) {
+            double s = 0.0;
+            for (int k = j; k < i; ++k) s += Lc[i * ld + k] * X[k * ld + j];
+            X[i * ld + j] = -s * dinv[i];
+        }
+    }
+    __syncwarp();
+    for (int d = 1; d < nb; ++d) {
+        for (int bj = 0; bj + d < nb; ++bj) {
+            const int bi = bj + d;
+            double t0 = 0.0, t1 = 0.0;
+            for (int bk = bj; bk < bi; ++bk) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    dmma(t0, t1, Lc[(8 * bi + g) * ld + 8 * bk + 4 * ks + q], X[(8 * bk + 4 * ks + q) * ld + 8 * bj + g]);
+            }
+            tile[g * 8 + 2 * q] = t0;
+            tile[g * 8 + 2 * q + 1] = t1;
+            __syncwarp();
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                dmma(x0, x1, -X[(8 * bi + g) * ld + 8 * bi + 4 * ks + q], tile[(4 * ks + q) * 8 + g]);
+            const int i = 8 * bi + g, j = 8 * bj + 2 * q;
+            if (i < T) { X[i * ld + j] = x0; X[i * ld + j + 1] = x1; }
+            __syncwarp();
+        }
+    }
+}
+
 template <bool TA, bool SYM>
 __device__ __forceinline__ void warp_mm(const double* __restrict__ A, const double* __restrict__ B,
                                         double* __restrict__ C, int T, int ld, int nt8, int nk4, int g, int q) {
@@ -66,7 +169,7 @@ __device__ __forceinline__ void warp_mm(const double* __restrict__ A, const doub
     }
 }
 
-__global__ void __launch_bounds__(PWMAX * 32)
+__global__ void __launch_bounds__(PWMAX * 32, 2)
 k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int N_b, int Tmax,
             int ld,
             const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ mu,
@@ -84,12 +187,14 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
     load_exp_table(etab);
     const int TP8 = (Tmax + 7) & ~7;
     const int asz = TP8 * ld;
-    double* A1 = sm + (size_t)wid * (3 * asz + Tmax * Q + 2 * Tmax);
+    double* A1 = sm + (size_t)wid * (3 * asz + Tmax * Q + 2 * Tmax + TP8 + 64);
     double* A2 = A1 + asz;
     double* A3 = A2 + asz;
     double* xs = A3 + asz;
     double* ev = xs + Tmax * Q;
     double* mw = ev + Tmax;
+    double* dinv = mw + Tmax;          // [TP8]
+    double* tile = dinv + TP8;         // [64]
     for (int e = lane; e < 3 * asz; e += 32) A1[e] = 0.0;
     __syncthreads();
     const int64_t* off2 = reinterpret_cast<const int64_t*>(ws + w.off2);   // (block layout only; unused when w.v2)
@@ -120,65 +225,54 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
         __syncwarp();
         // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) -------------------------------------------------
         const int ntri = T * (T + 1) / 2;
-        for (int e = lane; e < ntri; e += 32) {
+        {
             int i, j;
-            tri_index(e, i, j);
-            double k1 = 0.0, d2;
-            for (int cc = sp.n0; cc < nc; ++cc) k1 += osc[cc] * comp_value(sp, cc, xs + i * Q, xs + j * Q, hil2, d2, etab);
-            if (i == j) k1 += s_noise;
-            A1[i * ld + j] = k1;
-            A1[j * ld + i] = k1;
+            tri_index(lane, i, j);
+            for (int e = lane; e < ntri; e += 32) {
+                double k1 = 0.0, d2;
+                for (int cc = sp.n0; cc < nc; ++cc) k1 += osc[cc] * comp_one(sp, cc, xs + i * Q, xs + j * Q, hil2, etab, d2);
+                if (i == j) k1 += s_noise;
+                A1[i * ld + j] = k1;
+                A1[j * ld + i] = k1;
+                tri_step32(i, j);
+            }
         }
+        for (int e = lane; e < asz; e += 32) A2[e] = 0.0;
         __syncwarp();
-        // ---- Cholesky in place (right-looking, warp-synchronous) ----------------------------------------------------
-        for (int k = 0; k < T; ++k) {
-            const double dkk = A1[k * ld + k];
-            if (!(dkk > 0.0)) { if (lane == 0) atomicCAS(info + 2, 0, l * P_b + p + 1); }
-            const double d = sqrt(dkk), inv = 1.0 / d;
-            __syncwarp();
-            for (int i = k + lane; i < T; i += 32) A1[i * ld + k] = (i == k) ? d : A1[i * ld + k] * inv;
-            __syncwarp();
-            for (int i = k + 1 + lane; i < T; i += 32) {
-                const double lik = A1[i * ld + k];
-                for (int j = k + 1; j <= i; ++j) A1[i * ld + j] -= lik * A1[j * ld + k];
-            }
-            __syncwarp();
+        // ---- blocked Cholesky in place, L^-1 into A2 (tensor pipe for the block updates) ------------------------------------
+        {
+            const int bad = warp_cholesky(A1, T, ld, dinv, lane);
+            if (bad && lane == 0) atomicCAS(info + 2, 0, l * P_b + p + 1);
         }
-        for (int t = lane; t < T; t += 32) sC += 2.0 * log(A1[t * ld + t]);                                   // 192
-        // ---- L^-1 (lane per column, forward substitution) into A2 ----------------------------------------------------
-        for (int j = lane; j < T; j += 32) {
-            for (int i = 0; i < j; ++i) A2[i * ld + j] = 0.0;
-            A2[j * ld + j] = 1.0 / A1[j * ld + j];
-            for (int i = j + 1; i < T; ++i) {
-                double s0 = 0.0, s1 = 0.0;
-                int k = j;
-                for (; k + 1 < i; k += 2) { s0 += A1[i * ld + k] * A2[k * ld + j]; s1 += A1[i * ld + k + 1] * A2[(k + 1) * ld + j]; }
-                if (k < i) s0 += A1[i * ld + k] * A2[k * ld + j];
-                A2[i * ld + j] = -(s0 + s1) / A1[i * ld + i];
-            }
-        }
+        for (int t = lane; t < T; t += 32) sC -= 2.0 * log(dinv[t]);                                          // 192
+        warp_tri_inverse(A1, A2, T, ld, dinv, tile, lane);
         __syncwarp();
         if (w.v2) {   // rows of L^-1 for the fused pass: [row][k'], k' = column inside the subject, zero padded to TP
             double* gl = ws + w.Lrows + ((size_t)l * N_b + r0) * w.TP;
+            int i = 0, k = lane;
+            while (k >= w.TP) { k -= w.TP; ++i; }
             for (int e = lane; e < T * w.TP; e += 32) {
-                const int i = e / w.TP, k = e % w.TP;
                 gl[e] = (k <= i) ? A2[i * ld + k] : 0.0;
+                k += 32;
+                while (k >= w.TP) { k -= w.TP; ++i; }
             }
         }
         // ---- B^-1 = L^-T L^-1 into A3 --------------------------------------------------------------------------------
         warp_mm<true, true>(A2, A2, A3, T, ld, nt8, nk4, g, q);
         __syncwarp();
         // ---- K0_p (+ diag v) into A1 ; D1 ; adjoint of K0 = c B^-1 contracted on the fly (lower triangle, weight 2) ---
+        int ti_, tj_;
+        tri_index(lane, ti_, tj_);
         for (int e = lane; e < ntri; e += 32) {
-            int i, j;
-            tri_index(e, i, j);
+            const int i = ti_, j = tj_;
+            tri_step32(ti_, tj_);
             const double bi = A3[i * ld + j] * (i == j ? 1.0 : 2.0);
             double k0 = 0.0;
 #pragma unroll
             for (int cc = 0; cc < NCMAX; ++cc) {
                 if (cc < sp.n0) {
                     double d2;
-                    const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hil2, d2, etab);
+                    const double f = comp_one(sp, cc, xs + i * Q, xs + j * Q, hil2, etab, d2);
                     k0 += osc[cc] * f;
                     gos[cc] += bi * f;
                     if (sp.rbf_dim[cc] >= 0) gls[cc] += bi * f * d2;
@@ -213,16 +307,17 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
                 while (j >= T) { j -= T; ++i; }
             }
         }
+        tri_index(lane, ti_, tj_);
         for (int e = lane; e < ntri; e += 32) {
-            int i, j;
-            tri_index(e, i, j);
+            const int i = ti_, j = tj_;
+            tri_step32(ti_, tj_);
             const double bi = A3[i * ld + j];
             const double gB = (i == j) ? bi - A1[i * ld + i] : 2.0 * bi - (A1[i * ld + j] + A1[j * ld + i]);
 #pragma unroll
             for (int cc = 0; cc < NCMAX; ++cc) {
                 if (cc >= sp.n0 && cc < nc) {
                     double d2;
-                    const double f = comp_value(sp, cc, xs + i * Q, xs + j * Q, hil2, d2, etab);
+                    const double f = comp_one(sp, cc, xs + i * Q, xs + j * Q, hil2, etab, d2);
                     gos[cc] += gB * f;
                     if (sp.rbf_dim[cc] >= 0) gls[cc] += gB * f * d2;
                 }
@@ -268,7 +363,7 @@ static int ld_for(int Tmax) {
 
 static size_t warp_doubles(int Tm, int Q) {
     const int ld = ld_for(Tm), TP8 = (Tm + 7) & ~7;
-    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + 2 * Tm;
+    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + 2 * Tm + TP8 + 64;
 }
 
 static int warps_per_cta(int Tm, int Q) {

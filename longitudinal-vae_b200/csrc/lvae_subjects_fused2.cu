@@ -51,28 +51,31 @@ __device__ __forceinline__ void tri2(int e, int& i, int& j) {   // e-th element 
     j = e - i * (i + 1) / 2;
 }
 
+// Per-set shared memory, all at compile-time offsets from the set base (one live pointer instead of fifteen); the
+// covariate rows (the only Q-dependent block) come last.
 struct SetSmem {
-    double* B1;      // [RG][LD]  Kxz, then V
-    double* B2;      // [RG][LD]  U, then Y
-    double* Lg;      // [2][RG][LDL]
-    double* xs;      // [2][RG][Q]
-    double* mus;     // [2][RG]
-    double* bmu;     // [2][RG]
-    double* rpart;   // [SETW][RG]
-    double* upart;   // [SETW][RG]
-    double* rs;      // [RG]
-    double* us;      // [RG]
-    int* meta;       // [3][GT]
-    int* blo;        // [RG]
-    int* bhi;        // [RG]
+    double* sb;
+    __device__ __forceinline__ double* B1() const { return sb; }                          // [RG][LD]  Kxz, then V
+    __device__ __forceinline__ double* B2() const { return sb + RG * LD; }                // [RG][LD]  U, then Y
+    __device__ __forceinline__ double* Lg() const { return sb + 2 * RG * LD; }            // [2][RG][LDL]
+    __device__ __forceinline__ double* mus() const { return Lg() + 2 * RG * LDL; }        // [2][RG]
+    __device__ __forceinline__ double* bmu() const { return mus() + 2 * RG; }             // [2][RG]
+    __device__ __forceinline__ double* rpart() const { return bmu() + 2 * RG; }           // [SETW][RG]
+    __device__ __forceinline__ double* upart() const { return rpart() + SETW * RG; }      // [SETW][RG]
+    __device__ __forceinline__ double* rs() const { return upart() + SETW * RG; }         // [RG]
+    __device__ __forceinline__ double* us() const { return rs() + RG; }                   // [RG]
+    __device__ __forceinline__ int* meta() const { return reinterpret_cast<int*>(us() + RG); }   // [3][GT], 16-byte aligned
+    __device__ __forceinline__ int* blo() const { return meta() + 3 * GT; }               // [RG]
+    __device__ __forceinline__ int* bhi() const { return blo() + RG; }
+    __device__ __forceinline__ int* nlo() const { return bhi() + RG; }                    // same for the NEXT group
+    __device__ __forceinline__ int* nhi() const { return nlo() + RG; }
+    __device__ __forceinline__ double* xs() const { return us() + RG + (3 * GT + 4 * RG) / 2; }   // [2][RG][Q]
 };
+constexpr int SET_FIXED = 2 * RG * LD + 2 * RG * LDL + 4 * RG + 2 * SETW * RG + 2 * RG + (3 * GT + 4 * RG) / 2;
 
-__host__ __device__ inline size_t set_doubles(int Q) {
-    return 2 * (size_t)RG * LD + 2 * (size_t)RG * LDL + 2 * (size_t)RG * Q + 4 * RG + 2 * SETW * RG + 2 * RG +
-           (3 * GT + 2 * RG + 1) / 2 + 2;
-}
+__host__ __device__ inline size_t set_doubles(int Q) { return (size_t)SET_FIXED + 2 * (size_t)RG * Q; }
 __host__ __device__ inline size_t fused2_doubles(int Q, int nh) {
-    return (size_t)64 * LD + (size_t)64 * Q + 64 + (size_t)16 * (nh + 1) + 2 * 16 * 8 + 36 * 64 + 2 * set_doubles(Q);
+    return (size_t)64 * LD + 64 + 2 * 16 * 8 + 36 * 64 + (size_t)16 * (nh + 2) + (size_t)64 * Q + 2 * set_doubles(Q);
 }
 
 template <int NC0, int NC1>
@@ -87,28 +90,14 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     const int set = tid >> 8, lt = tid & 255, wid = tid >> 5, wl = wid & 7, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int nh = hyp_count(sp), MM = M * M;
 
-    double* p = sm;
-    double* const Wp = p; p += 64 * LD;
-    double* const zs = p; p += 64 * Q;
-    double* const av = p; p += 64;
-    double* const hyp = p; p += 16 * (nh + 1);
-    double* const cols = p; p += 2 * 16 * 8;
-    double* const sxch = p; p += 36 * 64;           // S exchange between the two sets at the end
-    p += (size_t)set * set_doubles(Q);
+    double* const Wp = sm;                           // [64][LD]
+    double* const av = Wp + 64 * LD;                 // [64]
+    double* const cols = av + 64;                    // [2][16][8]
+    double* const sxch = cols + 2 * 16 * 8;          // [36][64]  S exchange between the two sets at the end
+    double* const hyp = sxch + 36 * 64;              // [16][nh + 1]
+    double* const zs = hyp + 16 * (nh + 2) - ((16 * (nh + 2)) & 1);   // [64][Q]   (kept on an even double offset)
     SetSmem S;
-    S.B1 = p; p += RG * LD;
-    S.B2 = p; p += RG * LD;
-    S.Lg = p; p += 2 * RG * LDL;
-    S.xs = p; p += 2 * RG * Q;
-    S.mus = p; p += 2 * RG;
-    S.bmu = p; p += 2 * RG;
-    S.rpart = p; p += SETW * RG;
-    S.upart = p; p += SETW * RG;
-    S.rs = p; p += RG;
-    S.us = p; p += RG;
-    S.meta = reinterpret_cast<int*>(p);             // 16-byte aligned: every preceding block is an even count of doubles
-    S.blo = S.meta + 3 * GT;
-    S.bhi = S.blo + RG;
+    S.sb = zs + 64 * Q + (size_t)set * set_doubles(Q);
 
     // ---- per-CTA constants -------------------------------------------------------------------------------------------
     if (tid < sp.n_ls) { const double v = ls[(size_t)tid * L + l]; hil2[tid] = 0.5 / (v * v); il3[tid] = 1.0 / (v * v * v); }
@@ -132,12 +121,14 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     // this thread's Kxz / U / V / Y elements: rows 8*mt + g (mt = 0..2), columns 8*wl + 2q + {0,1}
     const int j0 = 8 * wl + 2 * q;
     // SYRK tiles of S owned by this warp (lower triangle of the 8 x 8 tile grid, 36 tiles over 8 warps)
-    int sti[5], stj[5];
     double sacc[5][2];
+    int so_i[5], so_j[5];                            // column offsets (8 * tile index) of the A and B fragments in U
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int e = wl + 8 * i;
-        if (e < 36) tri2(e, sti[i], stj[i]); else { sti[i] = -1; stj[i] = 0; }
+        int ti = 0, tj = 0;
+        if (e < 36) tri2(e, ti, tj);
+        so_i[i] = 8 * ti; so_j[i] = 8 * tj;
         sacc[i][0] = sacc[i][1] = 0.0;
     }
     double ng1acc[2] = {0.0, 0.0}, daacc[2] = {0.0, 0.0}, accA = 0.0;
@@ -147,36 +138,39 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
 #pragma unroll
     for (int k = 0; k < NC1; ++k) g1os[k] = g1ls[k] = 0.0;
 
-    // issue the prefetch of group `gi` (its meta entry must already be visible in smem slot `slot`) into data buffer `buf`
-    auto issue_data = [&](int slot, int buf) {
-        const int* mt_ = S.meta + slot * GT;
-        const int row0 = mt_[0], R = mt_[1];
-        for (int e = lt; e < RG * Q; e += 256) cp_async8(S.xs + buf * RG * Q + e, x + (size_t)row0 * Q + e, e < R * Q, x);
-        if (lt < RG) {
-            cp_async8(S.mus + buf * RG + lt, mu + (size_t)(row0 + lt) * L + l, lt < R, x);
-            cp_async8(S.bmu + buf * RG + lt, bmu_g + row0 + lt, lt < R, x);
+    // row -> [lo, hi) of its subject inside a group, from the group's meta entry
+    auto row_block = [&](const int* mt_, int t, int R, int& lo, int& hi) {
+        lo = t; hi = t;
+        if (t < R) {
+            lo = 0; hi = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s) { const int end = mt_[3 + s]; if (t >= end) lo = end; }
+#pragma unroll
+            for (int s = 4; s >= 0; --s) { const int end = mt_[3 + s]; if (t < end) hi = end; }
         }
-        for (int e = lt; e < RG * RG; e += 256) {
-            const int t = e / RG, k = e % RG;
-            int lo = 0, hi = 0;
-            if (t < R) {
+    };
+    // issue the prefetch of a group (meta entry visible in smem slot `slot`; nlo/nhi hold its row blocks) into buffer `buf`
+    auto issue_data = [&](int slot, int buf) {
+        const int* mt_ = S.meta() + slot * GT;
+        const int row0 = mt_[0], R = mt_[1];
+        for (int e = lt; e < RG * Q; e += 256) cp_async8(S.xs() + buf * RG * Q + e, x + (size_t)row0 * Q + e, e < R * Q, x);
+        if (lt < RG) {
+            cp_async8(S.mus() + buf * RG + lt, mu + (size_t)(row0 + lt) * L + l, lt < R, x);
+            cp_async8(S.bmu() + buf * RG + lt, bmu_g + row0 + lt, lt < R, x);
+        }
+        double* dst = S.Lg() + buf * RG * LDL;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) {
-                    const int end = mt_[3 + s];
-                    if (t >= end) lo = end;
-                }
-#pragma unroll
-                for (int s = 4; s >= 0; --s) {
-                    const int end = mt_[3 + s];
-                    if (t < end) hi = end;
-                }
+        for (int rep = 0; rep < 3; ++rep) {
+            const int e = lt + 256 * rep;
+            if (e < RG * RG) {
+                const int t = e / RG, k = e - t * RG;
+                const int lo = S.nlo()[t];
+                cp_async8(dst + t * LDL + k, Lrows + (size_t)(row0 + t) * TP + (k - lo), (k >= lo) && (k < S.nhi()[t]), x);
             }
-            const bool valid = (k >= lo) && (k < hi);
-            cp_async8(S.Lg + buf * RG * LDL + t * LDL + k, Lrows + (size_t)(row0 + t) * TP + (k - lo), valid, x);
         }
     };
     auto issue_meta = [&](int gi, int slot) {
-        if (lt < 2) cp_async16(S.meta + slot * GT + 4 * lt, gtab + (size_t)gi * GT + 4 * lt);
+        if (lt < 2) cp_async16(S.meta() + slot * GT + 4 * lt, gtab + (size_t)gi * GT + 4 * lt);
     };
 
     __syncthreads();
@@ -188,6 +182,8 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         cp_async_commit();
         cp_async_wait_all();
         set_barrier(set);
+        if (lt < RG) { int lo, hi; row_block(S.meta(), lt, S.meta()[1], lo, hi); S.nlo()[lt] = lo; S.nhi()[lt] = hi; }
+        set_barrier(set);
         issue_data(0, 0);
         cp_async_commit();
     }
@@ -198,27 +194,15 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         // ---- J0 ----------------------------------------------------------------------------------------------------------
         cp_async_wait_all();
         set_barrier(set);
-        const int* mt_ = S.meta + slot * GT;
+        const int* mt_ = S.meta() + slot * GT;
         const int row0 = mt_[0], R = mt_[1];
         const int R8 = (R + 7) & ~7, nmt = R8 >> 3, nk4 = (R + 3) >> 2;
-        const double* xs = S.xs + buf * RG * Q;
-        const double* mus = S.mus + buf * RG;
-        const double* Lg = S.Lg + buf * RG * LDL;
+        const double* xs = S.xs() + buf * RG * Q;
+        const double* mus = S.mus() + buf * RG;
+        const double* Lg = S.Lg() + buf * RG * LDL;
+        const bool more = gi + 2 < ngroups;
         if (lt < RG) {
-            int lo = lt, hi = lt;
-            if (lt < R) {
-                lo = 0; hi = 0;
-#pragma unroll
-                for (int s = 0; s < 5; ++s) { const int end = mt_[3 + s]; if (lt >= end) lo = end; }
-#pragma unroll
-                for (int s = 4; s >= 0; --s) { const int end = mt_[3 + s]; if (lt < end) hi = end; }
-            }
-            S.blo[lt] = lo; S.bhi[lt] = hi;
-        }
-        if (gi + 2 < ngroups) {
-            issue_data((it + 1) % 3, buf ^ 1);
-            if (gi + 4 < ngroups) issue_meta(gi + 4, (it + 2) % 3);
-            cp_async_commit();
+            S.blo()[lt] = S.nlo()[lt]; S.bhi()[lt] = S.nhi()[lt];          // planned when this group was prefetched
         }
 
         // ---- J1: Kxz from covariates ; f_c in registers ; partial dots of r --------------------------------------------------
@@ -226,47 +210,55 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
 #pragma unroll
         for (int mt = 0; mt < NMT; ++mt) {
             const int t = 8 * mt + g;
-            double kx[2] = {0.0, 0.0};
+            const bool rv = t < R;
+            double kx0 = 0.0, kx1 = 0.0;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = j0 + e;
-                const bool valid = (t < R) && (j < M);
-#pragma unroll
-                for (int cc = 0; cc < NC0; ++cc) {
-                    double d2, f = 0.0;
-                    if (valid) f = comp_value(sp, cc, xs + t * Q, zs + j * Q, hil2, d2, etab);
-                    fc[mt][e][cc] = f;
-                    kx[e] += osc[cc] * f;
-                }
+            for (int cc = 0; cc < NC0; ++cc) {
+                double f0, f1, d0, d1;
+                comp_pair(sp, cc, xs + t * Q, zs + j0 * Q, zs + (j0 + 1) * Q, hil2, etab, f0, f1, d0, d1);
+                f0 = (rv && j0 < M) ? f0 : 0.0;
+                f1 = (rv && j0 + 1 < M) ? f1 : 0.0;
+                fc[mt][0][cc] = f0; fc[mt][1][cc] = f1;
+                kx0 += osc[cc] * f0; kx1 += osc[cc] * f1;
             }
-            *reinterpret_cast<double2*>(S.B1 + t * LD + j0) = make_double2(kx[0], kx[1]);
-            double pr = kx[0] * av[j0] + kx[1] * av[j0 + 1];
+            *reinterpret_cast<double2*>(S.B1() + t * LD + j0) = make_double2(kx0, kx1);
+            double pr = kx0 * av[j0] + kx1 * av[j0 + 1];
             pr += __shfl_xor_sync(0xffffffffu, pr, 1);
             pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-            if (q == 0) S.rpart[wl * RG + t] = pr;
+            if (q == 0) S.rpart()[wl * RG + t] = pr;
         }
         set_barrier(set);
+        // prefetch of the next group of this set (its meta entry arrived with this group's data)
+        if (more) {
+            const int* nm = S.meta() + ((it + 1) % 3) * GT;
+            if (lt < RG) { int lo, hi; row_block(nm, lt, nm[1], lo, hi); S.nlo()[lt] = lo; S.nhi()[lt] = hi; }
+        }
 
         // ---- J2: U = L^-1 Kxz (rows of a tile only see k <= row, inside their subject) ; r -----------------------------------------
         if (lt < RG) {
             double s = -mus[lt];
 #pragma unroll
-            for (int ww = 0; ww < SETW; ++ww) s += S.rpart[ww * RG + lt];
-            S.rs[lt] = s;
+            for (int ww = 0; ww < SETW; ++ww) s += S.rpart()[ww * RG + lt];
+            S.rs()[lt] = s;
         }
 #pragma unroll
         for (int mt = 0; mt < NMT; ++mt) {
             const int t = 8 * mt + g;
             double u0 = 0.0, u1 = 0.0;
             if (mt < nmt) {
-                const int klo = S.blo[8 * mt] >> 2;
-                const int khi = min(2 * mt + 2, (S.bhi[min(8 * mt + 7, R - 1)] + 3) >> 2);
+                const int klo = S.blo()[8 * mt] >> 2;
+                const int khi = min(2 * mt + 2, (S.bhi()[min(8 * mt + 7, R - 1)] + 3) >> 2);
                 for (int ks = klo; ks < khi; ++ks)
-                    dmma(u0, u1, Lg[t * LDL + 4 * ks + q], S.B1[(4 * ks + q) * LD + 8 * wl + g]);
+                    dmma(u0, u1, Lg[t * LDL + 4 * ks + q], S.B1()[(4 * ks + q) * LD + 8 * wl + g]);
             }
-            *reinterpret_cast<double2*>(S.B2 + t * LD + j0) = make_double2(u0, u1);
+            *reinterpret_cast<double2*>(S.B2() + t * LD + j0) = make_double2(u0, u1);
         }
         set_barrier(set);
+        if (more) {
+            issue_data((it + 1) % 3, buf ^ 1);
+            if (gi + 4 < ngroups) issue_meta(gi + 4, (it + 2) % 3);
+            cp_async_commit();
+        }
 
         // ---- J3: V = L^-T U -> B1 ; ng1 ; partial dots of u ; S += U^T U ------------------------------------------------------
 #pragma unroll
@@ -274,34 +266,33 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
             const int t = 8 * mt + g;
             double v0 = 0.0, v1 = 0.0;
             if (mt < nmt) {
-                const int khi = (S.bhi[min(8 * mt + 7, R - 1)] + 3) >> 2;
+                const int khi = (S.bhi()[min(8 * mt + 7, R - 1)] + 3) >> 2;
                 for (int ks = 2 * mt; ks < khi; ++ks)
-                    dmma(v0, v1, Lg[(4 * ks + q) * LDL + 8 * mt + g], S.B2[(4 * ks + q) * LD + 8 * wl + g]);
+                    dmma(v0, v1, Lg[(4 * ks + q) * LDL + 8 * mt + g], S.B2()[(4 * ks + q) * LD + 8 * wl + g]);
             }
-            *reinterpret_cast<double2*>(S.B1 + t * LD + j0) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(S.B1() + t * LD + j0) = make_double2(v0, v1);
             const double mt_mu = mus[t];
             ng1acc[0] += v0 * mt_mu;
             ng1acc[1] += v1 * mt_mu;
             double pu = v0 * av[j0] + v1 * av[j0 + 1];
             pu += __shfl_xor_sync(0xffffffffu, pu, 1);
             pu += __shfl_xor_sync(0xffffffffu, pu, 2);
-            if (q == 0) S.upart[wl * RG + t] = pu;
+            if (q == 0) S.upart()[wl * RG + t] = pu;
         }
         for (int ks = 0; ks < nk4; ++ks) {
-            const double* Urow = S.B2 + (4 * ks + q) * LD + g;
+            const double* Urow = S.B2() + (4 * ks + q) * LD + g;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                if (sti[i] >= 0) dmma(sacc[i][0], sacc[i][1], Urow[8 * sti[i]], Urow[8 * stj[i]]);
-            }
+            for (int i = 0; i < 4; ++i) dmma(sacc[i][0], sacc[i][1], Urow[so_i[i]], Urow[so_j[i]]);
+            if (wl < 4) dmma(sacc[4][0], sacc[4][1], Urow[so_i[4]], Urow[so_j[4]]);
         }
         set_barrier(set);
 
         // ---- J4: u = V a - B^-1 mu ; Y = V W ---------------------------------------------------------------------------------
         if (lt < RG) {
-            double s = -S.bmu[buf * RG + lt];
+            double s = -S.bmu()[buf * RG + lt];
 #pragma unroll
-            for (int ww = 0; ww < SETW; ++ww) s += S.upart[ww * RG + lt];
-            S.us[lt] = lt < R ? s : 0.0;
+            for (int ww = 0; ww < SETW; ++ww) s += S.upart()[ww * RG + lt];
+            S.us()[lt] = lt < R ? s : 0.0;
         }
         double yacc[NMT][2];
 #pragma unroll
@@ -311,7 +302,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
             const double b_ = Wp[(4 * ks + q) * LD + 8 * wl + g];
 #pragma unroll
             for (int mt = 0; mt < NMT; ++mt) {
-                if (mt < nmt) dmma(yacc[mt][0], yacc[mt][1], S.B1[(8 * mt + g) * LD + 4 * ks + q], b_);
+                if (mt < nmt) dmma(yacc[mt][0], yacc[mt][1], S.B1()[(8 * mt + g) * LD + 4 * ks + q], b_);
             }
         }
         set_barrier(set);
@@ -320,7 +311,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
 #pragma unroll
         for (int mt = 0; mt < NMT; ++mt) {
             const int t = 8 * mt + g;
-            const double ut = S.us[t];
+            const double ut = S.us()[t];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int j = j0 + e;
@@ -339,11 +330,11 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
                 }
                 daacc[e] += kx * ut;
             }
-            *reinterpret_cast<double2*>(S.B2 + t * LD + j0) = make_double2(yacc[mt][0], yacc[mt][1]);
+            *reinterpret_cast<double2*>(S.B2() + t * LD + j0) = make_double2(yacc[mt][0], yacc[mt][1]);
         }
         if (lt < R) {
-            accA += S.rs[lt] * S.us[lt];
-            d_mu[(size_t)(row0 + lt) * L + l] = -2.0 * c * S.us[lt];
+            accA += S.rs()[lt] * S.us()[lt];
+            d_mu[(size_t)(row0 + lt) * L + l] = -2.0 * c * S.us()[lt];
         }
         set_barrier(set);
 
@@ -351,10 +342,10 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         if (wl < 6) {
             int jt, i;
             tri2(wl, jt, i);                                 // i <= jt
-            if (jt < nmt && 8 * jt < S.bhi[min(8 * i + 7, R - 1)]) {
+            if (jt < nmt && 8 * jt < S.bhi()[min(8 * i + 7, R - 1)]) {
                 double q0 = 0.0, q1 = 0.0;
-                const double* Ya = S.B2 + (8 * i + g) * LD + q;
-                const double* Vb = S.B1 + (8 * jt + g) * LD + q;
+                const double* Ya = S.B2() + (8 * i + g) * LD + q;
+                const double* Vb = S.B1() + (8 * jt + g) * LD + q;
 #pragma unroll 4
                 for (int ks = 0; ks < 16; ++ks) dmma(q0, q1, Ya[4 * ks], Vb[4 * ks]);
                 const int t = 8 * i + g;
@@ -362,14 +353,14 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int t2 = 8 * jt + 2 * q + e;
-                    if (t < R && t2 < R && S.blo[t] == S.blo[t2]) {
-                        const double gB = -wgt * (c * S.us[t] * S.us[t2] + (e ? q1 : q0));
+                    if (t < R && t2 < R && S.blo()[t] == S.blo()[t2]) {
+                        const double gB = -wgt * (c * S.us()[t] * S.us()[t2] + (e ? q1 : q0));
                         if (t == t2) gno += gB;
 #pragma unroll
                         for (int k = 0; k < NC1; ++k) {
                             const int cc = sp.n0 + k;
                             double d2;
-                            const double f = comp_value(sp, cc, xs + t * Q, xs + t2 * Q, hil2, d2, etab);
+                            const double f = comp_one(sp, cc, xs + t * Q, xs + t2 * Q, hil2, etab, d2);
                             g1os[k] += gB * f;
                             if (sp.rbf_dim[cc] >= 0) g1ls[k] += gB * f * d2;
                         }
@@ -415,7 +406,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         if (set == 1) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                if (sti[i] >= 0) {
+                if (wl + 8 * i < 36) {
                     double* d = sxch + (wl + 8 * i) * 64 + g * 8 + 2 * q;
                     d[0] = sacc[i][0]; d[1] = sacc[i][1];
                 }
@@ -426,15 +417,15 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     if (set == 0) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            if (sti[i] >= 0) {
+            if (wl + 8 * i < 36) {
                 const double* d = sxch + (wl + 8 * i) * 64 + g * 8 + 2 * q;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int ii = 8 * sti[i] + g, jj = 8 * stj[i] + 2 * q + e;
+                    const int ii = so_i[i] + g, jj = so_j[i] + 2 * q + e;
                     if (ii < M && jj < M) {
                         const double v = sacc[i][e] + d[e];
                         part[stats_off_S() + (size_t)ii * M + jj] = v;
-                        if (sti[i] != stj[i]) part[stats_off_S() + (size_t)jj * M + ii] = v;
+                        if (so_i[i] != so_j[i]) part[stats_off_S() + (size_t)jj * M + ii] = v;
                     }
                 }
             }
