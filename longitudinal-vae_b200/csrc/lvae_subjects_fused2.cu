@@ -51,8 +51,13 @@ __device__ __forceinline__ void tri2(int e, int& i, int& j) {   // e-th element 
     j = e - i * (i + 1) / 2;
 }
 
-// Per-set shared memory, all at compile-time offsets from the set base (one live pointer instead of fifteen); the
-// covariate rows (the only Q-dependent block) come last.
+// Covariates are kept GATHERED per component: slot 4*c + 0 holds the column of component c's squared-exponential factor,
+// slots 4*c + 1..3 the columns of its categorical/binary factors (unused slots are zero).  XC[slot][row] for the rows of a
+// group (all components, per set, double-buffered, filled by cp.async), ZC[slot][column] for the inducing points (K0
+// components, per CTA).  Every inner-loop address is then base + compile-time offset.
+constexpr int CS = 4;
+
+// Per-set shared memory, all at compile-time offsets from the set base; the size-dependent blocks (XC, FC) come last.
 struct SetSmem {
     double* sb;
     __device__ __forceinline__ double* B1() const { return sb; }                          // [RG][LD]  Kxz, then V
@@ -69,23 +74,27 @@ struct SetSmem {
     __device__ __forceinline__ int* bhi() const { return blo() + RG; }
     __device__ __forceinline__ int* nlo() const { return bhi() + RG; }                    // same for the NEXT group
     __device__ __forceinline__ int* nhi() const { return nlo() + RG; }
-    __device__ __forceinline__ double* xs() const { return us() + RG + (3 * GT + 4 * RG) / 2; }   // [2][RG][Q]
+    __device__ __forceinline__ double* XC() const { return us() + RG + (3 * GT + 4 * RG) / 2; }   // [2][NCT*CS][RG]
 };
 constexpr int SET_FIXED = 2 * RG * LD + 2 * RG * LDL + 4 * RG + 2 * SETW * RG + 2 * RG + (3 * GT + 4 * RG) / 2;
 
-__host__ __device__ inline size_t set_doubles(int Q) { return (size_t)SET_FIXED + 2 * (size_t)RG * Q; }
-__host__ __device__ inline size_t fused2_doubles(int Q, int nh) {
-    return (size_t)64 * LD + 64 + 2 * 16 * 8 + 36 * 64 + (size_t)16 * (nh + 2) + (size_t)64 * Q + 2 * set_doubles(Q);
+__host__ __device__ inline size_t set_doubles(int nct, int nr) {
+    return (size_t)SET_FIXED + 2 * (size_t)nct * CS * RG + (size_t)nr * RG * LD;
+}
+__host__ __device__ inline size_t common_doubles(int nc0, int nct, int nh) {
+    return (size_t)64 * LD + 64 + 2 * 16 * 8 + (size_t)16 * (nh + 2) + (size_t)nc0 * CS * 64 + (size_t)(nct * CS + 2) / 2 + 2;
 }
 
 template <int NC0, int NC1>
 __global__ void __launch_bounds__(512, 1)
 k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b, int TP,
-                  const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ z,
+                  int NR, const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ z,
                   const double* __restrict__ ls, const double* __restrict__ os, double c, double* __restrict__ d_mu,
                   double* __restrict__ ws) {
     extern __shared__ double sm[];
     __shared__ double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
+    constexpr int NCT = NC0 + NC1;
+    constexpr int XCSZ = NCT * CS * RG;
     const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
     const int set = tid >> 8, lt = tid & 255, wid = tid >> 5, wl = wid & 7, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int nh = hyp_count(sp), MM = M * M;
@@ -93,23 +102,37 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     double* const Wp = sm;                           // [64][LD]
     double* const av = Wp + 64 * LD;                 // [64]
     double* const cols = av + 64;                    // [2][16][8]
-    double* const sxch = cols + 2 * 16 * 8;          // [36][64]  S exchange between the two sets at the end
-    double* const hyp = sxch + 36 * 64;              // [16][nh + 1]
-    double* const zs = hyp + 16 * (nh + 2) - ((16 * (nh + 2)) & 1);   // [64][Q]   (kept on an even double offset)
+    double* const hyp = cols + 2 * 16 * 8;           // [16][nh + 1]
+    double* const ZC = hyp + ((16 * (nh + 2)) & ~1); // [NC0*CS][64]
+    int* const dimtab = reinterpret_cast<int*>(ZC + NC0 * CS * 64);   // [NCT*CS]
+    double* const sets = ZC + NC0 * CS * 64 + ((NCT * CS + 2) / 2) + ((((NCT * CS + 2) / 2) & 1));
     SetSmem S;
-    S.sb = zs + 64 * Q + (size_t)set * set_doubles(Q);
+    S.sb = sets + (size_t)set * set_doubles(NCT, NR);
+    double* const FC = S.XC() + 2 * XCSZ;            // [NR][RG][LD]  un-scaled values of the SE-bearing K0 components
+    double* const sxch = sets + set_doubles(NCT, NR);   // set 1's B1|B2 (36*64 doubles), reused at the very end
 
     // ---- per-CTA constants -------------------------------------------------------------------------------------------
     if (tid < sp.n_ls) { const double v = ls[(size_t)tid * L + l]; hil2[tid] = 0.5 / (v * v); il3[tid] = 1.0 / (v * v * v); }
     if (tid < sp.n0 + sp.n1) osc[tid] = os[(size_t)tid * L + l];
     load_exp_table(etab);
+    if (tid < NCT * CS) {
+        const int cc = tid / CS, sl = tid % CS;
+        int dim = -1;
+        if (sl == 0) dim = sp.rbf_dim[cc];
+        else if (sl - 1 < sp.n_mask[cc]) dim = sp.mask_dim[cc][sl - 1];
+        dimtab[tid] = dim;
+    }
+    __syncthreads();
     {
         const double* Wl = ws + w.W + (size_t)l * MM;
         for (int e = tid; e < 64 * LD; e += 512) {
             const int i = e / LD, j = e % LD;
             Wp[e] = (i < M && j < M) ? Wl[i * M + j] : 0.0;
         }
-        for (int e = tid; e < 64 * Q; e += 512) zs[e] = (e < M * Q) ? z[(size_t)l * M * Q + e] : 0.0;
+        for (int e = tid; e < NC0 * CS * 64; e += 512) {
+            const int sl = e >> 6, j = e & 63, dim = dimtab[sl];
+            ZC[e] = (dim >= 0 && j < M) ? z[((size_t)l * M + j) * Q + dim] : 0.0;
+        }
         if (tid < 64) av[tid] = tid < M ? ws[w.a + (size_t)l * M + tid] : 0.0;
         for (int e = tid; e < 16 * (nh + 1); e += 512) hyp[e] = 0.0;
     }
@@ -118,8 +141,9 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     const double* Lrows = ws + w.Lrows + (size_t)l * N_b * TP;
     const double* bmu_g = ws + w.bmu + (size_t)l * N_b;
 
-    // this thread's Kxz / U / V / Y elements: rows 8*mt + g (mt = 0..2), columns 8*wl + 2q + {0,1}
+    // this thread's Kxz / U / V / Y elements: rows 8*mt + g (mt = 0..2), columns j0 = 8*wl + 2q and j0 + 1
     const int j0 = 8 * wl + 2 * q;
+    const bool cv0 = j0 < M, cv1 = j0 + 1 < M;
     // SYRK tiles of S owned by this warp (lower triangle of the 8 x 8 tile grid, 36 tiles over 8 warps)
     double sacc[5][2];
     int so_i[5], so_j[5];                            // column offsets (8 * tile index) of the A and B fragments in U
@@ -153,7 +177,15 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     auto issue_data = [&](int slot, int buf) {
         const int* mt_ = S.meta() + slot * GT;
         const int row0 = mt_[0], R = mt_[1];
-        for (int e = lt; e < RG * Q; e += 256) cp_async8(S.xs() + buf * RG * Q + e, x + (size_t)row0 * Q + e, e < R * Q, x);
+        double* xc = S.XC() + buf * XCSZ;
+#pragma unroll
+        for (int rep = 0; rep < (XCSZ + 255) / 256; ++rep) {
+            const int e = lt + 256 * rep;
+            if (e < XCSZ) {
+                const int sl = e / RG, t = e - sl * RG, dim = dimtab[sl];
+                cp_async8(xc + e, x + (size_t)(row0 + t) * Q + dim, (t < R) && (dim >= 0), x);
+            }
+        }
         if (lt < RG) {
             cp_async8(S.mus() + buf * RG + lt, mu + (size_t)(row0 + lt) * L + l, lt < R, x);
             cp_async8(S.bmu() + buf * RG + lt, bmu_g + row0 + lt, lt < R, x);
@@ -197,7 +229,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         const int* mt_ = S.meta() + slot * GT;
         const int row0 = mt_[0], R = mt_[1];
         const int R8 = (R + 7) & ~7, nmt = R8 >> 3, nk4 = (R + 3) >> 2;
-        const double* xs = S.xs() + buf * RG * Q;
+        const double* xc = S.XC() + buf * XCSZ;
         const double* mus = S.mus() + buf * RG;
         const double* Lg = S.Lg() + buf * RG * LDL;
         const bool more = gi + 2 < ngroups;
@@ -205,21 +237,38 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
             S.blo()[lt] = S.nlo()[lt]; S.bhi()[lt] = S.nhi()[lt];          // planned when this group was prefetched
         }
 
-        // ---- J1: Kxz from covariates ; f_c in registers ; partial dots of r --------------------------------------------------
-        double fc[NMT][2][NC0];
+        // ---- J1: Kxz from the gathered covariates ; SE-bearing f_c -> FC (smem) ; partial dots of r ---------------------------
 #pragma unroll
         for (int mt = 0; mt < NMT; ++mt) {
             const int t = 8 * mt + g;
             const bool rv = t < R;
             double kx0 = 0.0, kx1 = 0.0;
+            int fslot = 0;
 #pragma unroll
             for (int cc = 0; cc < NC0; ++cc) {
-                double f0, f1, d0, d1;
-                comp_pair(sp, cc, xs + t * Q, zs + j0 * Q, zs + (j0 + 1) * Q, hil2, etab, f0, f1, d0, d1);
-                f0 = (rv && j0 < M) ? f0 : 0.0;
-                f1 = (rv && j0 + 1 < M) ? f1 : 0.0;
-                fc[mt][0][cc] = f0; fc[mt][1][cc] = f1;
-                kx0 += osc[cc] * f0; kx1 += osc[cc] * f1;
+                bool on0 = rv && cv0, on1 = rv && cv1;
+#pragma unroll
+                for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
+                    if (i < sp.n_mask[cc]) {
+                        const double a = xc[(cc * CS + 1 + i) * RG + t];
+                        const double2 b = *reinterpret_cast<const double2*>(ZC + (cc * CS + 1 + i) * 64 + j0);
+                        if (sp.mask_type[cc][i] == LVAE_CAT) { on0 = on0 && (a - b.x == 0.0); on1 = on1 && (a - b.y == 0.0); }
+                        else { on0 = on0 && (a + b.x == 2.0); on1 = on1 && (a + b.y == 2.0); }
+                    }
+                }
+                double f0 = on0 ? 1.0 : 0.0, f1 = on1 ? 1.0 : 0.0;
+                if (sp.rbf_dim[cc] >= 0) {
+                    const double a = xc[(cc * CS) * RG + t], h = hil2[sp.ls_idx[cc]];
+                    const double2 b = *reinterpret_cast<const double2*>(ZC + (cc * CS) * 64 + j0);
+                    const double t0 = a - b.x, t1 = a - b.y;
+                    const double e0 = exp_neg(-(t0 * t0) * h, etab), e1 = exp_neg(-(t1 * t1) * h, etab);
+                    f0 = on0 ? e0 : 0.0;
+                    f1 = on1 ? e1 : 0.0;
+                    *reinterpret_cast<double2*>(FC + fslot * RG * LD + t * LD + j0) = make_double2(f0, f1);
+                    ++fslot;
+                }
+                kx0 += osc[cc] * f0;
+                kx1 += osc[cc] * f1;
             }
             *reinterpret_cast<double2*>(S.B1() + t * LD + j0) = make_double2(kx0, kx1);
             double pr = kx0 * av[j0] + kx1 * av[j0 + 1];
@@ -228,7 +277,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
             if (q == 0) S.rpart()[wl * RG + t] = pr;
         }
         set_barrier(set);
-        // prefetch of the next group of this set (its meta entry arrived with this group's data)
+        // row blocks of the next group of this set (its meta entry arrived with this group's data)
         if (more) {
             const int* nm = S.meta() + ((it + 1) % 3) * GT;
             if (lt < RG) { int lo, hi; row_block(nm, lt, nm[1], lo, hi); S.nlo()[lt] = lo; S.nhi()[lt] = hi; }
@@ -311,25 +360,42 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
 #pragma unroll
         for (int mt = 0; mt < NMT; ++mt) {
             const int t = 8 * mt + g;
+            const bool rv = t < R;
             const double ut = S.us()[t];
+            const double gb0 = 2.0 * c * ut * av[j0] + 2.0 * yacc[mt][0];
+            const double gb1 = 2.0 * c * ut * av[j0 + 1] + 2.0 * yacc[mt][1];
+            double kx0 = 0.0, kx1 = 0.0;
+            int fslot = 0;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = j0 + e;
-                const double gbar = 2.0 * c * ut * av[j] + 2.0 * yacc[mt][e];
-                double kx = 0.0;
+            for (int cc = 0; cc < NC0; ++cc) {
+                double f0, f1;
+                if (sp.rbf_dim[cc] >= 0) {
+                    const double2 f = *reinterpret_cast<const double2*>(FC + fslot * RG * LD + t * LD + j0);
+                    ++fslot;
+                    f0 = f.x; f1 = f.y;
+                    const double a = xc[(cc * CS) * RG + t];
+                    const double2 b = *reinterpret_cast<const double2*>(ZC + (cc * CS) * 64 + j0);
+                    const double t0 = a - b.x, t1 = a - b.y;
+                    gls[cc] += gb0 * f0 * (t0 * t0) + gb1 * f1 * (t1 * t1);
+                } else {
+                    bool on0 = rv && cv0, on1 = rv && cv1;
 #pragma unroll
-                for (int cc = 0; cc < NC0; ++cc) {
-                    const double f = fc[mt][e][cc];
-                    kx += osc[cc] * f;
-                    gos[cc] += gbar * f;
-                    const int rd = sp.rbf_dim[cc];
-                    if (rd >= 0) {
-                        const double d = xs[t * Q + rd] - zs[j * Q + rd];
-                        gls[cc] += gbar * f * (d * d);
+                    for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
+                        if (i < sp.n_mask[cc]) {
+                            const double a = xc[(cc * CS + 1 + i) * RG + t];
+                            const double2 b = *reinterpret_cast<const double2*>(ZC + (cc * CS + 1 + i) * 64 + j0);
+                            if (sp.mask_type[cc][i] == LVAE_CAT) { on0 = on0 && (a - b.x == 0.0); on1 = on1 && (a - b.y == 0.0); }
+                            else { on0 = on0 && (a + b.x == 2.0); on1 = on1 && (a + b.y == 2.0); }
+                        }
                     }
+                    f0 = on0 ? 1.0 : 0.0; f1 = on1 ? 1.0 : 0.0;
                 }
-                daacc[e] += kx * ut;
+                gos[cc] += gb0 * f0 + gb1 * f1;
+                kx0 += osc[cc] * f0;
+                kx1 += osc[cc] * f1;
             }
+            daacc[0] += kx0 * ut;
+            daacc[1] += kx1 * ut;
             *reinterpret_cast<double2*>(S.B2() + t * LD + j0) = make_double2(yacc[mt][0], yacc[mt][1]);
         }
         if (lt < R) {
@@ -358,11 +424,23 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
                         if (t == t2) gno += gB;
 #pragma unroll
                         for (int k = 0; k < NC1; ++k) {
-                            const int cc = sp.n0 + k;
-                            double d2;
-                            const double f = comp_one(sp, cc, xs + t * Q, xs + t2 * Q, hil2, etab, d2);
+                            const int cc = NC0 + k;
+                            bool on = true;
+#pragma unroll
+                            for (int i2 = 0; i2 < LVAE_MAX_MASKS; ++i2) {
+                                if (i2 < sp.n_mask[cc]) {
+                                    const double a = xc[(cc * CS + 1 + i2) * RG + t], b = xc[(cc * CS + 1 + i2) * RG + t2];
+                                    on = on && ((sp.mask_type[cc][i2] == LVAE_CAT) ? (a - b == 0.0) : (a + b == 2.0));
+                                }
+                            }
+                            double f = on ? 1.0 : 0.0;
+                            if (sp.rbf_dim[cc] >= 0) {
+                                const double dd = xc[(cc * CS) * RG + t] - xc[(cc * CS) * RG + t2];
+                                const double d2 = dd * dd;
+                                f = on ? exp_neg(-d2 * hil2[sp.ls_idx[cc]], etab) : 0.0;
+                                g1ls[k] += gB * f * d2;
+                            }
                             g1os[k] += gB * f;
-                            if (sp.rbf_dim[cc] >= 0) g1ls[k] += gB * f * d2;
                         }
                     }
                 }
@@ -386,7 +464,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         }
 #pragma unroll
         for (int k = 0; k < NC1; ++k) {
-            const int cc = sp.n0 + k;
+            const int cc = NC0 + k;
             const double s1 = warp_sum(g1os[k]);
             const double s2 = warp_sum(g1ls[k]);
             if (lane == 0) {
@@ -404,6 +482,7 @@ k_subjects_fused2(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
             if (g == 0) { cols[(0 * 16 + wid) * 8 + 2 * q + e] = a2; cols[(1 * 16 + wid) * 8 + 2 * q + e] = b2; }
         }
         if (set == 1) {
+            set_barrier(set);                                // every warp of set 1 is done with its B1 | B2
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 if (wl + 8 * i < 36) {
@@ -494,14 +573,16 @@ __global__ void __launch_bounds__(256) k_plan_groups(const int32_t* __restrict__
 
 template <int NC0, int NC1>
 int launch2(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
-    const size_t smem = sizeof(double) * fused2_doubles(p->Q, w.nh);
+    int nr = 0;
+    for (int cc = 0; cc < sp.n0; ++cc) nr += sp.rbf_dim[cc] >= 0;
+    const size_t smem = sizeof(double) * (common_doubles(NC0, NC0 + NC1, w.nh) + 2 * set_doubles(NC0 + NC1, nr));
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_subjects_fused2<NC0, NC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         attr = smem;
     }
-    k_subjects_fused2<NC0, NC1><<<dim3(w.nchunk, p->L), 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, w.TP, p->x, p->mu,
+    k_subjects_fused2<NC0, NC1><<<dim3(w.nchunk, p->L), 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, w.TP, nr, p->x, p->mu,
                                                                         p->z, p->lengthscale, p->outputscale,
                                                                         0.5 * p->scale, p->d_mu, p->workspace);
     LVAE_COUNT_LAUNCH();
@@ -511,8 +592,12 @@ int launch2(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
 }  // namespace
 
 bool lvae_fused2_supported(const lvae_kld_problem_t* p) {
-    return p->M <= 64 && p->T_max <= RG && p->ks.n_comp0 >= 1 && p->ks.n_comp0 <= 4 && p->ks.n_comp1 >= 1 &&
-           p->ks.n_comp1 <= 2 && p->Q <= 10;
+    if (!(p->M <= 64 && p->T_max <= RG && p->ks.n_comp0 >= 1 && p->ks.n_comp0 <= 4 && p->ks.n_comp1 >= 1 &&
+          p->ks.n_comp1 <= 2 && p->ks.spec))
+        return false;
+    int nr = 0;                                  // SE-bearing K0 components keep their values in shared memory
+    for (int cc = 0; cc < p->ks.n_comp0; ++cc) nr += p->ks.spec[(size_t)cc * LVAE_SPEC_STRIDE] >= 0;
+    return nr <= 3;
 }
 
 int lvae_plan_groups_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st) {
