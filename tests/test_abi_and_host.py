@@ -1,0 +1,116 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/lvae_b200.h declares (no compute calls without a
+GPU); host-side logic: kernel-structure flattening (block-indexing rule), samplers, workspace sizing, loud failure."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    import __graft_entry__ as ge
+    lib_path = ge.build()
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "lvae_b200.h")).read()
+    declared = set(re.findall(r"\b(lvae_[a-z0-9_]+)\s*\(", header))
+    declared -= {"lvae_kernel_spec_t", "lvae_kld_problem_t"}
+    assert len(declared) >= 14
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/lvae_b200.h but not exported"
+    from lvae_b200 import _lib
+    assert set(_lib.EXPORTS) <= declared
+
+
+def test_block_indexing_rule_is_bit_exact():
+    """kernel_gen.py:225-308: order cat, sqexp, bin, cat_int, bin_int; K1 iff id cat or cat_int on the id covariate."""
+    import lvae_oracle as orc
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200.spec import build_structure, flatten
+    from lvae_b200 import synth, GP_model
+    lists_all = [synth.kernel_lists(c) for c in ("cfg1", "cfg2", "cfg4")] + [dict(
+        cat_kernel=[2, 3], bin_kernel=[5], sqexp_kernel=[0, 1],
+        cat_int_kernel=[{'cont_covariate': 1, 'cat_covariate': 2}, {'cont_covariate': 0, 'cat_covariate': 3}],
+        bin_int_kernel=[{'cont_covariate': 1, 'bin_covariate': 5}], covariate_missing_val=[{'covariate': 1, 'mask': 4}])]
+    for lists in lists_all:
+        k0, k1 = orc.parse_kernel_lists(3, **lists, id_covariate=2)
+        for gen in (generate_kernel_batched, GP_model.generate_kernel_batched):
+            cm0, cm1 = gen(3, **lists, id_covariate=2)
+            st, ls, os_ = build_structure(flatten(cm0), flatten(cm1), 3)
+            assert (st.n_comp0, st.n_comp1) == (len(k0), len(k1))
+            for row, comp in zip(st.table, k0 + k1):
+                rbf = [d for kind, d in comp.factors if kind == 'rbf']
+                masks = [(0 if kind == 'cat' else 1, d) for kind, d in comp.factors if kind != 'rbf']
+                assert row[0] == (rbf[0] if rbf else -1)
+                assert row[2] == len(masks)
+                assert [(row[3 + 2 * i], row[4 + 2 * i]) for i in range(len(masks))] == masks
+            assert st.n_ls == sum(len(c.lengthscales) for c in k0 + k1)
+            assert torch.allclose(ls, torch.full_like(ls, 2.5), rtol=1e-6)            # kernel_spec.py:68 / GP_model.py:60
+            assert torch.allclose(os_, torch.full_like(os_, float(np.log(2.0))), rtol=1e-6)
+
+
+def test_state_dict_keys_follow_gpytorch_layout():
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200 import synth
+    cm0, cm1 = generate_kernel_batched(4, **synth.kernel_lists("cfg2"), id_covariate=2)
+    keys = set(cm0.state_dict().keys())
+    assert "kernels.0.raw_outputscale" in keys and "kernels.0.base_kernel.raw_lengthscale" in keys
+    assert "kernels.1.base_kernel.kernels.1.raw_lengthscale" in keys
+    assert cm0.kernels[0].base_kernel.raw_lengthscale.shape == (4, 1, 1)
+    assert cm0.kernels[0].raw_outputscale.shape == (4,)
+
+
+def test_product_ops_fail_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200 import synth, elbo_functions as EF
+    from lvae_b200.likelihoods import GaussianLikelihood
+    b = synth.make_batch("cfg1", P=2, L=2, M=5)
+    cm0, cm1 = generate_kernel_batched(2, **b.lists, id_covariate=2)
+    with pytest.raises(RuntimeError):
+        cm0(b.x, b.z).evaluate()
+    with pytest.raises(RuntimeError):
+        EF.minibatch_KLD_upper_bound(cm0, cm1, GaussianLikelihood(batch_shape=torch.Size([2])), 2, b.m, b.H, b.x, b.mu,
+                                     b.log_v, b.z, 2, 2, 20, True, 1e-6)
+
+
+def test_samplers_match_reference_golden():
+    """utils.py:40-113 — bit-exact row indices and batch composition under the same numpy seed."""
+    from lvae_b200.utils import SubjectSampler, VaryingLengthBatchSampler, VaryingLengthSubjectSampler
+    from torch.utils.data.sampler import BatchSampler
+    s = dict(np.load(os.path.join(ROOT, "tests", "golden", "samplers.npz")))
+    for k in range(3):
+        P, T, spb = (int(v) for v in s[f"fixed{k}_PTspb"])
+        np.random.seed(100 + k)
+        rows = list(iter(SubjectSampler(list(range(P * T)), P, T)))
+        assert rows == s[f"fixed{k}_rows"].tolist()
+        assert [len(b) for b in BatchSampler(rows, spb * T, drop_last=False)] == s[f"fixed{k}_batch_lens"].tolist()
+    ids = s["vary_ids"]
+    data = [{'label': torch.tensor([0.0, 0.0, float(i)])} for i in ids]
+    for k in range(2):
+        vs = VaryingLengthSubjectSampler(data, 2)
+        np.random.seed(200 + k)
+        batches = list(iter(VaryingLengthBatchSampler(vs, int(s[f"vary{k}_spb"]))))
+        assert [i for b in batches for i in b] == s[f"vary{k}_flat"].tolist()
+        assert [len(b) for b in batches] == s[f"vary{k}_batch_lens"].tolist()
+
+
+def test_group_by_subject_matches_boolean_mask_grouping():
+    """elbo_functions.py:264-267 on CPU tensors (pure torch host logic)."""
+    import lvae_oracle as orc
+    from lvae_b200.elbo_functions import group_by_subject
+    rng = np.random.default_rng(1)
+    ids = rng.integers(0, 9, size=60).astype(np.float64)
+    order, offsets, T_max, sum_T2 = group_by_subject(torch.from_numpy(ids))
+    uniq, rows = orc.group_rows_by_subject(ids)
+    assert np.array_equal(order.numpy(), np.concatenate(rows))
+    lens = np.array([len(r) for r in rows])
+    assert np.array_equal(offsets.numpy(), np.concatenate([[0], np.cumsum(lens)]))
+    assert T_max == lens.max() and sum_T2 == int((lens * lens).sum())
+    sorted_ids = np.sort(ids)
+    order2, *_ = group_by_subject(torch.from_numpy(sorted_ids))
+    assert order2 is None

@@ -1,0 +1,66 @@
+"""GPU, >= 2 devices (gpurun --gpus 2): subjects sharded over two ranks, statistics all-reduced over NCCL — bound, natural
+gradients and hyper-gradients must equal the single-GPU result; d_mu rows follow their owner."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, case, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200 import distributed as D
+    from helpers import build_modules, constrained_param_grads
+    g = load_golden(case)
+    dev = f"cuda:{rank}"
+    L = g["mu"].shape[1]
+    lo, hi, _ = D.shard_rows(g["offsets"], rank, world)
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    cm0, cm1, lik = build_modules(g["lists"], L, g["lengthscale"], g["outputscale"], g["noise"], dev)
+    mu = t("mu")[lo:hi].clone().requires_grad_(True)
+    lv = t("log_v")[lo:hi].clone().requires_grad_(True)
+    P_b = len(g["offsets"]) - 1
+    D.enable()
+    if bool(g["ragged"]):
+        kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, t("m"), t("H"), t("x")[lo:hi], mu, lv, t("z"),
+                                                        int(g["P_tot"]), P_b, int(g["N_tot"]), True, 2, float(g["eps"]))
+    else:
+        kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, t("m"), t("H"), t("x")[lo:hi], mu, lv, t("z"),
+                                                   int(g["P_tot"]), P_b, int(g["T"]), True, float(g["eps"]))
+    kld.sum().backward()
+    D.disable()
+    torch.save(dict(kld=float(kld.sum().item()), gm=gm.cpu(), gH=gH.cpu(), d_mu=mu.grad.cpu(), lo=lo, hi=hi,
+                    d_hyper=constrained_param_grads(cm0, cm1, lik)), os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["cfg2_small", "cfg4_ragged"])
+def test_two_rank_sharding_matches_reference(case, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from helpers import golden_hyper_vector, rel
+    mp.spawn(_worker, args=(2, 29700 + os.getpid() % 200, case, str(tmp_path)), nprocs=2, join=True)
+    g = load_golden(case)
+    outs = [torch.load(os.path.join(str(tmp_path), f"r{r}.pt"), weights_only=False) for r in range(2)]
+    for o in outs:
+        assert abs(o["kld"] - float(g["kld"])) <= 1e-6 * abs(float(g["kld"]))
+        assert rel(o["gm"], g["grad_m"]) < 1e-6 and rel(o["gH"], g["grad_H"]) < 1e-6
+        ref = golden_hyper_vector(g)
+        assert np.abs(o["d_hyper"] - ref).max() <= 1e-6 * np.abs(ref).max()
+        assert rel(o["d_mu"], g["d_mu"][o["lo"]:o["hi"]]) < 1e-6
+    assert outs[0]["hi"] == outs[1]["lo"]
