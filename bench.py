@@ -184,8 +184,28 @@ def time_cpu(b, n_subjects, steps, warmup):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line there.  Park fd 1 on stderr and keep
+    the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,7 +230,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
@@ -413,7 +433,7 @@ def main():
                 "finite": finite}
         if lat:
             line["latency_point"] = lat
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
