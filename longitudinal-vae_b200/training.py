@@ -1,5 +1,18 @@
-"""Host side of the Hensman minibatch step (training.py:108-135): the natural-gradient update of (m, H)."""
+"""Host side of the Hensman minibatch loop (training.py:15-237) over the CUDA GP-prior ops.
+
+`hensman_training` keeps the reference's positional signature and return tuple.  The step body follows
+training.py:90-140 line by line; the three library calls on the hot path are `minibatch_KLD_upper_bound[_iter]`,
+autograd through it, and `natural_gradient_step` (training.py:129-135 as one launch reusing the H^-1 the bound already
+computed).  The periodic validation / test-set MSE / checkpoint block (training.py:150-235) belongs to the reference's
+evaluation code (out of scope): it is reduced to an optional `on_validation(epoch, state)` callback.
+"""
+import numpy as np
+import torch
+from torch.utils.data.sampler import BatchSampler
+
 from . import ops
+from .elbo_functions import minibatch_KLD_upper_bound, minibatch_KLD_upper_bound_iter
+from .utils import HensmanDataLoader, SubjectSampler, VaryingLengthBatchSampler, VaryingLengthSubjectSampler
 
 
 def natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr, check=False):
@@ -13,3 +26,80 @@ def natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr, check=False
     if check and int(info[3].item()) != 0:
         raise RuntimeError(f"cholesky: natural-gradient update of latent {int(info[3].item()) - 1} is not positive-definite")
     return m2.detach(), H2.detach()
+
+
+def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL, num_samples, latent_dim, covar_module0,
+                     covar_module1, likelihoods, m, H, zt_list, P, T, varying_T, Q, weight, id_covariate, loss_function,
+                     natural_gradient=False, natural_gradient_lr=0.01, subjects_per_batch=20, memory_dbg=False,
+                     eps=1e-6, results_path=None, validation_dataset=None, generation_dataset=None,
+                     prediction_dataset=None, gp_model=None, csv_file_test_data=None, csv_file_test_label=None,
+                     test_mask_file=None, data_source_path=None, num_workers=4, on_validation=None, verbose=True):
+    """Minibatch SVI training [Hensman et al. 2013] of the L-VAE (training.py:15-237).  Returns
+    (penalty_term_arr, net_train_loss_arr, nll_loss_arr, recon_loss_arr, kld_loss_arr, m, H, best_epoch)."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    N = len(dataset)
+    assert type_KL == 'GPapprox_closed'
+    if varying_T:                                                                               # training.py:69-75
+        n_batches = (P + subjects_per_batch - 1) // subjects_per_batch
+        sampler = VaryingLengthBatchSampler(VaryingLengthSubjectSampler(dataset, id_covariate), subjects_per_batch)
+    else:
+        batch_size = subjects_per_batch * T
+        n_batches = (P * T + batch_size - 1) // batch_size
+        sampler = BatchSampler(SubjectSampler(dataset, P, T), batch_size, drop_last=False)
+    dataloader = HensmanDataLoader(dataset, batch_sampler=sampler, num_workers=num_workers)
+
+    curves = {k: [] for k in ("net", "recon", "nll", "kld", "penalty")}
+    best_epoch = 0
+    for epoch in range(1, epochs + 1):
+        sums = dict(net=0.0, recon=0.0, nll=0.0, kld=0.0)
+        for sample_batched in dataloader:
+            optimiser.zero_grad()
+            nnet_model.train()
+            covar_module0.train()
+            covar_module1.train()
+            data = sample_batched['digit'].double().to(device)
+            train_x = sample_batched['label'].double().to(device)
+            mask = sample_batched['mask'].double().to(device)
+            N_batch = data.shape[0]
+
+            recon_batch, mu, log_var = nnet_model(data)                                          # 103 (stock PyTorch VAE)
+            recon_loss, nll = nnet_model.loss_function(recon_batch, data, mask)
+            recon_loss, nll_loss = torch.sum(recon_loss), torch.sum(nll)
+            PSD_H = H if natural_gradient else torch.matmul(H, H.transpose(-1, -2))              # 108
+            if varying_T:                                                                        # 110-115
+                P_in_current_batch = torch.unique(train_x[:, id_covariate]).shape[0]
+                kld_loss, grad_m, grad_H = minibatch_KLD_upper_bound_iter(
+                    covar_module0, covar_module1, likelihoods, latent_dim, m, PSD_H, train_x, mu, log_var, zt_list, P,
+                    P_in_current_batch, N, natural_gradient, id_covariate, eps)
+            else:
+                P_in_current_batch = N_batch // T
+                kld_loss, grad_m, grad_H = minibatch_KLD_upper_bound(
+                    covar_module0, covar_module1, likelihoods, latent_dim, m, PSD_H, train_x, mu, log_var, zt_list, P,
+                    P_in_current_batch, T, natural_gradient, eps)
+            recon_loss = recon_loss * P / P_in_current_batch                                     # 117-124
+            nll_loss = nll_loss * P / P_in_current_batch
+            if loss_function == 'nll':
+                net_loss = nll_loss + kld_loss
+            elif loss_function == 'mse':
+                kld_loss = kld_loss / latent_dim
+                net_loss = recon_loss + weight * kld_loss
+            net_loss.sum().backward()                                                            # 126-127
+            optimiser.step()
+            if natural_gradient:                                                                 # 129-135
+                m, H = natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr)
+            vals = torch.stack([net_loss.detach().sum(), recon_loss.detach(), nll_loss.detach(),
+                                kld_loss.detach().sum()]).tolist()                               # one sync instead of four (137-140)
+            for k, v in zip(("net", "recon", "nll", "kld"), vals):
+                sums[k] += v / n_batches
+        if verbose:
+            print('Iter %d/%d - Loss: %.3f  - GP loss: %.3f  - NLL Loss: %.3f  - Recon Loss: %.3f' % (
+                epoch, epochs, sums["net"], sums["kld"], sums["nll"], sums["recon"]), flush=True)
+        curves["penalty"].append(0.0)
+        for k in ("net", "recon", "nll", "kld"):
+            curves[k].append(sums[k])
+        if (not epoch % 25) and epoch != epochs and on_validation is not None:                    # 150-235 (callback)
+            if on_validation(epoch, dict(nnet_model=nnet_model, covar_module0=covar_module0, covar_module1=covar_module1,
+                                         likelihoods=likelihoods, zt_list=zt_list, m=m, H=H)):
+                best_epoch = epoch
+    arr = lambda k: np.asarray(curves[k], dtype=np.float64)
+    return arr("penalty"), arr("net"), arr("nll"), arr("recon"), arr("kld"), m, H, best_epoch
