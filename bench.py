@@ -334,6 +334,7 @@ def main():
     out_kld = torch.empty(1, dtype=torch.float64).pin_memory()
     if dist is not None:
         EF.set_process_group(dist.group.WORLD)
+    EF.set_error_check("deferred")          # no device sync inside the op; failures still raise (check_errors below)
     state = {"m": m, "H": H}
 
     def e2e_step():
@@ -369,6 +370,8 @@ def main():
     e2e_val = P_b * world / (e2e_ms * 1e-3)
     h2d = (hx.numel() + hmu.numel() + hlv.numel()) * 8
     d2h = (out_mu.numel() + out_lv.numel() + 1) * 8
+    EF.check_errors()
+    EF.set_error_check("immediate")
     EF.set_process_group(None)
 
     lat = None

@@ -44,6 +44,11 @@ __device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int 
     const int g = lane >> 2, q = lane & 3;
     const int nb = (T + 7) >> 3;
     int bad = 0;
+    // lane -> (ur, uc), 1 <= uc <= ur <= 7: its element of the 7 x 7 lower triangle updated inside a diagonal block
+    int ur = 0;
+    while ((ur + 1) * (ur + 2) / 2 <= lane) ++ur;
+    const int uc = lane - ur * (ur + 1) / 2 + 1;
+    ur += 1;
     for (int kb = 0; kb < nb; ++kb) {
         const int k0 = 8 * kb, bs = min(8, T - k0);
         for (int k = 0; k < bs; ++k) {
@@ -54,13 +59,8 @@ __device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int 
             if (lane == k) { A[(k0 + k) * ld + k0 + k] = akk * ri; dinv[k0 + k] = ri; }
             if (lane > k && lane < bs) A[(k0 + lane) * ld + k0 + k] *= ri;
             __syncwarp();
-            if (lane < 28) {
-                int r = 0;
-                while ((r + 1) * (r + 2) / 2 <= lane) ++r;
-                const int c_ = lane - r * (r + 1) / 2 + 1;
-                r += 1;
-                if (c_ > k && r < bs) A[(k0 + r) * ld + k0 + c_] -= A[(k0 + r) * ld + k0 + k] * A[(k0 + c_) * ld + k0 + k];
-            }
+            if (lane < 28 && uc > k && ur < bs)
+                A[(k0 + ur) * ld + k0 + uc] -= A[(k0 + ur) * ld + k0 + k] * A[(k0 + uc) * ld + k0 + k];
             __syncwarp();
         }
         if (kb + 1 < nb) {

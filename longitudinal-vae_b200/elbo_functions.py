@@ -15,6 +15,8 @@ from .spec import build_structure, flatten
 
 _GROUP = None        # torch.distributed process group over which the minibatch subjects are sharded (None = 1 GPU)
 _PATH = 0            # 0 auto, 1 generic kernels, 2 fused DMMA kernel
+_CHECK = "immediate"  # Cholesky-failure check: "immediate" (one device sync per call, like torch.cholesky) | "deferred"
+_PENDING = []        # KldCall objects whose info flags have not been read yet (deferred mode)
 
 
 def set_process_group(group):
@@ -26,6 +28,21 @@ def set_process_group(group):
 def set_kernel_path(path):
     global _PATH
     _PATH = int(path)
+
+
+def set_error_check(mode):
+    """"immediate": raise inside the call (costs one device->host sync per step, as torch.cholesky does in the reference).
+    "deferred": never block; a failed factorisation makes kld NaN and raises at the next call or at check_errors()."""
+    global _CHECK
+    if mode not in ("immediate", "deferred"):
+        raise ValueError(mode)
+    _CHECK = mode
+
+
+def check_errors():
+    """Raise if any earlier deferred call hit a non-positive-definite block."""
+    while _PENDING:
+        _PENDING.pop(0).raise_on_info()
 
 
 def _noise_of(likelihood, L, dtype, device):
@@ -48,8 +65,12 @@ class _KldBound(torch.autograd.Function):
         if _GROUP is not None:
             torch.distributed.all_reduce(call.stats, group=_GROUP)      # SVGP sufficient statistics over NVLink
         call.tail()
-        if meta.get("check", True):
+        if _CHECK == "immediate":
             call.raise_on_info()
+        else:
+            _PENDING.append(call)
+            if len(_PENDING) > 2:                      # the oldest one finished long ago: reading its flags does not stall
+                _PENDING.pop(0).raise_on_info()
         kld = call.kld_per_latent.sum()
         ctx.call = call
         ctx.ng = meta["natural_gradient"]

@@ -58,8 +58,11 @@ class Kernel(torch.nn.Module):
                  lengthscale_constraint=None, eps=1e-6, **kwargs):
         super().__init__()
         self._batch_shape = torch.Size(batch_shape)
-        if active_dims is not None and not torch.is_tensor(active_dims):
-            active_dims = torch.tensor(active_dims, dtype=torch.long)
+        self._dim_int = None                      # host copy of the covariate column (no device sync on the hot path)
+        if active_dims is not None:
+            self._dim_int = int(torch.as_tensor(active_dims).reshape(-1)[0])
+            if not torch.is_tensor(active_dims):
+                active_dims = torch.tensor(active_dims, dtype=torch.long)
         self.register_buffer("active_dims", active_dims)
         self.ard_num_dims = ard_num_dims
         self.eps = eps
@@ -89,9 +92,11 @@ class Kernel(torch.nn.Module):
         return self
 
     def _dim(self):
-        if self.active_dims is None:
-            raise ValueError("lvae_b200: leaf kernels need active_dims (a covariate column)")
-        return int(self.active_dims.reshape(-1)[0])
+        if self._dim_int is None:
+            if self.active_dims is None:
+                raise ValueError("lvae_b200: leaf kernels need active_dims (a covariate column)")
+            self._dim_int = int(self.active_dims.reshape(-1)[0])
+        return self._dim_int
 
     def forward(self, x1, x2, **params):
         return evaluate_dense(self, x1, x2)

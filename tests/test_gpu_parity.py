@@ -133,6 +133,16 @@ def test_non_pd_block_raises_like_torch_cholesky():
     P_b, T = len(g["offsets"]) - 1, int(g["T"])
     with pytest.raises(RuntimeError):
         EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, t("m"), H, t("x"), t("mu"), t("log_v"), t("z"), 15, P_b, T, True, 1e-6)
+    # deferred mode: the call itself does not block; the failure surfaces at check_errors() and the bound is NaN
+    EF.set_error_check("deferred")
+    try:
+        kld, _, _ = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, t("m"), H, t("x"), t("mu"), t("log_v"), t("z"), 15, P_b,
+                                                 T, True, 1e-6)
+        assert not torch.isfinite(kld)
+        with pytest.raises(RuntimeError):
+            EF.check_errors()
+    finally:
+        EF.set_error_check("immediate")
 
 
 def test_iter_handles_ungrouped_rows_bit_exact_grouping():
