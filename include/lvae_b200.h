@@ -71,7 +71,19 @@ int lvae_kernel_blocks_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int
                            const double* lengthscale, const double* outputscale, const double* diag_add, double* out,
                            void* stream);
 
+/* Batched GEMM on the FP64 tensor pipe: C[b] (m x n) = alpha * op(A[b]) op(B[b]) + beta * C[b], row-major — replaces the
+ * torch.matmul / einsum contractions of elbo_functions.py:183-184,189,194,208-214 when M > 64.
+ * op(A) is m x k: trans_a == 0 reads A[i*lda + kk], else A[kk*lda + i]; likewise op(B) (k x n).
+ * flags: LVAE_GEMM_LOWER computes only entries j <= i; LVAE_GEMM_MIRROR also stores C[j][i] (needs beta == 0). */
+#define LVAE_GEMM_LOWER 1
+#define LVAE_GEMM_MIRROR 2
+int lvae_gemm_batched_f64(int32_t trans_a, int32_t trans_b, int32_t m, int32_t n, int32_t k, double alpha, const double* A,
+                          int32_t lda, int64_t stride_a, const double* B, int32_t ldb, int64_t stride_b, double beta,
+                          double* C, int32_t ldc, int64_t stride_c, int32_t batch, int32_t flags, void* stream);
+
 /* Batched Cholesky, in place, lower, n <= 256: replaces torch.cholesky (elbo_functions.py:177,179,185).
+ * n <= 64: one CTA per matrix; n > 64: blocked by 64 (diagonal blocks in shared memory, panels and trailing updates as
+ * batched DMMA GEMMs; scratch from the stream-ordered allocator).
  * info: device int32[1], set to 1 + index of the first non-PD matrix (never cleared). */
 int lvae_potrf_batched_f64(double* A, int32_t n, int64_t batch_stride, int32_t batch, int32_t* info, void* stream);
 /* Explicit inverse from the Cholesky factor: replaces cholesky_solve(I, L) (elbo_functions.py:178,180,186). */

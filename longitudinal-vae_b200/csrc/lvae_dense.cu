@@ -3,6 +3,7 @@
 // parity tests on kernel matrices and Cholesky factors; the training hot path never materialises Kxz (see
 // lvae_subjects_fused.cu).  The dense kernel is HBM-write-bound: 8*L*n1*n2 bytes out, covariates stay in L1/L2.
 #include "lvae_host.h"
+#include "lvae_blas.h"
 #include "lvae_linalg.cuh"
 
 int64_t& lvae_launch_counter() {
@@ -181,6 +182,7 @@ extern "C" int lvae_potrf_batched_f64(double* A, int32_t n, int64_t batch_stride
                                       void* stream) {
     if (n <= 0 || n > LVAE_MAX_M || batch < 0 || batch_stride < (int64_t)n * n) return LVAE_E_BADARG;
     if (batch == 0) return 0;
+    if (n > 64) return lvae_potrf_big_abi(A, n, batch_stride, batch, info, (cudaStream_t)stream);
     k_potrf<<<batch, 256, 0, (cudaStream_t)stream>>>(A, n, batch_stride, info);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
@@ -191,6 +193,7 @@ extern "C" int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n,
     if (n <= 0 || n > LVAE_MAX_M || batch < 0 || batch_stride < (int64_t)n * n) return LVAE_E_BADARG;
     if (batch == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (n > 64) return lvae_potri_big_abi(Lc, Ainv, n, batch_stride, batch, st);
     double* tmp = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&tmp, sizeof(double) * (size_t)batch * n * n, st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);

@@ -170,3 +170,21 @@ def ng_step(m, H, grad_m, grad_H, lr, Hinv=None):
 
 def launch_count():
     return int(_lib.load().lvae_launch_count())
+
+
+def gemm_batched(A, B, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, C=None, flags=0):
+    """C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b] on the FP64 tensor pipe (lvae_gemm_batched_f64).  A, B: [batch, r, c]
+    contiguous.  flags: 1 = lower triangle only, 3 = lower computed and mirrored (symmetric results)."""
+    lib = require_cuda(A, B)
+    A, B = _c(A), _c(B)
+    batch = A.shape[0]
+    m, k = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
+    n = B.shape[1] if trans_b else B.shape[2]
+    if C is None:
+        C = torch.zeros(batch, m, n, dtype=F64, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.lvae_gemm_batched_f64(int(trans_a), int(trans_b), m, n, k, float(alpha), ptr(A), A.shape[2],
+                                       A.shape[1] * A.shape[2], ptr(B), B.shape[2], B.shape[1] * B.shape[2], float(beta),
+                                       ptr(C), n, m * n, batch, int(flags), stream_ptr(A.device))
+    check(rc, "lvae_gemm_batched_f64")
+    return C
