@@ -270,7 +270,7 @@ def main():
     T_max, sum_T2 = int(Tl.max()), int((Tl * Tl).sum())
     const = L * (N_b * world) / 2 if ragged else L * P_tot * int(b.T) / 2
     call = ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path)
-    ng_ws = torch.empty(4 * L * M * M, dtype=torch.float64, device=device)
+    ng_ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=torch.float64, device=device)
     ng_info = torch.zeros(4, dtype=torch.int32, device=device)
     lr = 1e-3
 

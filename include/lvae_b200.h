@@ -97,7 +97,8 @@ typedef struct {
     int32_t L, M, Q, P_b, N_b, T_max; /* P_b, N_b: subjects / rows held by THIS GPU; T_max = max rows per subject */
     int64_t sum_T2;                   /* sum_p T_p^2 over this GPU's subjects */
     int32_t natural_gradient; /* 1: emit grad_m/grad_H (elbo_functions.py:208-214); 0: emit d_m/d_H (autograd) */
-    int32_t path;             /* 0 = auto, 1 = generic kernels, 2 = fused DMMA kernel (M <= 64 only) */
+    int32_t path;             /* 0 = auto (fused DMMA kernel for M <= 64, GEMM-based path for 64 < M <= 256), 1 = generic kernels,
+                                 2 = force the fused kernel (M <= 64 only) */
     double scale;             /* P_tot / P_b                                           (elbo_functions.py:204) */
     double const_term;        /* L*P_tot*T/2 (204) or L*N/2 (299), subtracted once     */
     double eps;               /* jitter on Kzz only (176)                               */
@@ -145,10 +146,11 @@ int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream);
 
 /* Natural-gradient update of (m, H), in place (training.py:129-135).  Hinv: optional [L,M,M] H^-1 already computed by
  * lvae_kld_head_f64 for the same H (at workspace + lvae_kld_hinv_offset()); NULL recomputes it (training.py:130-131).
- * workspace: 4*L*M*M doubles (used for M > 64 only); info[3]. */
+ * workspace: lvae_ng_workspace_doubles(L, M) doubles (scratch of the blocked factorisation when M > 64); info[3]. */
 int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hinv, double lr,
                      int32_t L, int32_t M, double* workspace, int32_t* info, void* stream);
 int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p);
+int64_t lvae_ng_workspace_doubles(int32_t L, int32_t M);
 
 /* Optional per-phase device timing with CUDA events on the launch stream (bench.py's roofline leg).
  * phase: 0 head, 1 prep, 2 subjects, 3 reduce, 4 tail, 5 ng_step.  lvae_profile_last_ms synchronises on the event. */

@@ -9,28 +9,103 @@
 
 namespace {
 
-// mode 0: factor the diagonal block kb in place and invert the factor; mode 1: the block already holds the factor.
+// Cholesky of a tall panel (nr rows x 64 columns, row stride SLD, nr a multiple of 8): the 64 x 64 top block is factored
+// and every row below is solved against it, 8 columns at a time: warp 0 factors the 8 x 8 diagonal block, one thread per
+// row does the forward substitution, DMMA updates the remaining columns of the panel.  Same arithmetic as s_cholesky
+// (lvae_small.cuh), so the blocked factorisation rounds like an un-blocked one (no explicit block inverses in the solves:
+// they cost a factor cond(L_kk) in accuracy on the nearly singular Kzz of the reference).
+__device__ inline int s_cholesky_tall(double* __restrict__ A, int nr, double* __restrict__ dinv, int* flag) {
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int nrb = nr >> 3;
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+    for (int kb = 0; kb < 8; ++kb) {
+        const int k0 = 8 * kb;
+        if (wid == 0) {
+            for (int k = 0; k < 8; ++k) {
+                const double akk = A[(k0 + k) * SLD + k0 + k];
+                if (!(akk > 0.0) && lane == 0 && *flag == 0) *flag = k0 + k + 1;
+                double ri = rsqrt(akk);
+                ri = ri * (1.5 - 0.5 * akk * ri * ri);
+                const double d = akk * ri;
+                __syncwarp();
+                if (lane == k) { A[(k0 + k) * SLD + k0 + k] = d; dinv[k0 + k] = ri; }
+                if (lane > k && lane < 8) A[(k0 + lane) * SLD + k0 + k] *= ri;
+                __syncwarp();
+                if (lane < 28) {
+                    int r, c_;
+                    tri_ij(lane, r, c_);
+                    r += 1; c_ += 1;
+                    if (c_ > k && r < 8) A[(k0 + r) * SLD + k0 + c_] -= A[(k0 + r) * SLD + k0 + k] * A[(k0 + c_) * SLD + k0 + k];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int r = k0 + 8 + tid; r < nr; r += blockDim.x) {
+            double xr[8];
+#pragma unroll
+            for (int c_ = 0; c_ < 8; ++c_) {
+                double s = A[r * SLD + k0 + c_];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < c_) s -= xr[k] * A[(k0 + c_) * SLD + k0 + k];
+                xr[c_] = s * dinv[k0 + c_];
+            }
+#pragma unroll
+            for (int c_ = 0; c_ < 8; ++c_) A[r * SLD + k0 + c_] = xr[c_];
+        }
+        __syncthreads();
+        // trailing update inside the panel: tiles (ti, tj), kb < tj <= min(ti, 7), kb < ti < nrb
+        const int ncol = 7 - kb;                                   // remaining column blocks
+        const int nrow = nrb - kb - 1;                             // remaining row blocks
+        for (int tl = wid; tl < nrow * ncol; tl += (blockDim.x >> 5)) {
+            const int ti = kb + 1 + tl / ncol, tj = kb + 1 + tl % ncol;
+            if (tj > ti) continue;
+            double* Ct = A + (8 * ti + g) * SLD + 8 * tj + 2 * q;
+            double c0 = Ct[0], c1 = Ct[1];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const double a = -A[(8 * ti + g) * SLD + k0 + 4 * ks + q];
+                const double b = A[(8 * tj + g) * SLD + k0 + 4 * ks + q];
+                dmma884(c0, c1, a, b);
+            }
+            Ct[0] = c0; Ct[1] = c1;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < 64 * 64; e += blockDim.x) {
+        const int i = e >> 6, j = e & 63;
+        if (j > i) A[i * SLD + j] = 0.0;
+    }
+    __syncthreads();
+    return *flag;
+}
+
+// mode 0: factor the panel below and including diagonal block kb in place (rows 64 kb .. np-1, columns of the block) and
+// invert the 64 x 64 factor block; mode 1: the block already holds the factor (inverse only).
 __global__ void __launch_bounds__(512, 1)
 k_diag_block(double* __restrict__ F, int np, int kb, double* __restrict__ dinv_out, int mode, int32_t* info, int info_mod) {
     extern __shared__ double sm[];
     __shared__ double dinv[64];
     __shared__ int flag;
     const int b = blockIdx.x, tid = threadIdx.x, nb = np >> 6;
-    double* A = sm;
-    double* X = A + SMAT;
+    const int nr = mode == 0 ? np - 64 * kb : 64;
+    double* A = sm;                              // [nr][SLD]
+    double* X = A + (size_t)nr * SLD;
     double* scratch = X + SMAT;
     double* blk = F + (size_t)b * np * np + (size_t)(64 * kb) * np + 64 * kb;
-    for (int e = tid; e < 64 * 64; e += 512) {
+    for (int e = tid; e < nr * 64; e += 512) {
         const int i = e >> 6, j = e & 63;
         A[i * SLD + j] = (mode == 0 || j <= i) ? blk[(size_t)i * np + j] : 0.0;
     }
     __syncthreads();
     if (mode == 0) {
-        const int rc = s_cholesky(A, 64, dinv, &flag);
-        if (rc && tid == 0 && info) atomicCAS(info, 0, (info_mod > 0 ? b % info_mod : b) + 1);
-        for (int e = tid; e < 64 * 64; e += 512) {
+        const int rc = s_cholesky_tall(A, nr, dinv, &flag);
+        if (rc && tid == 0 && info) atomicCAS(info + (info_mod > 0 ? b / info_mod : 0), 0, (info_mod > 0 ? b % info_mod : b) + 1);
+        for (int e = tid; e < nr * 64; e += 512) {
             const int i = e >> 6, j = e & 63;
-            blk[(size_t)i * np + j] = A[i * SLD + j];               // strict upper of the block is zero now
+            blk[(size_t)i * np + j] = A[i * SLD + j];               // strict upper of the top block is zero now
         }
     } else {
         if (tid < 64) dinv[tid] = 1.0 / A[tid * SLD + tid];
@@ -72,9 +147,11 @@ __global__ void k_pad_out(double* __restrict__ dst, const double* __restrict__ s
 
 int diag_launch(double* F, int np, int kb, int batch, double* dinv, int mode, int32_t* info, int info_mod, cudaStream_t st) {
     static bool attr = false;
-    const size_t smem = sizeof(double) * (2 * SMAT + 16 * 64);
+    const size_t smem_max = sizeof(double) * ((size_t)256 * SLD + SMAT + 16 * 64);
+    const int nr = mode == 0 ? np - 64 * kb : 64;
+    const size_t smem = sizeof(double) * ((size_t)nr * SLD + SMAT + 16 * 64);
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         attr = true;
     }
@@ -93,16 +170,10 @@ int lvae_potrf_big(double* F, int np, int batch, double* dinv, int32_t* info_slo
         if (rc) return rc;
         const int k0 = 64 * kb, rem = np - k0 - 64;
         if (rem <= 0) break;
-        GemmDesc p;                                   // panel: P <- P D^-T  (in place; every CTA reads only the rows it writes)
-        p.A = F + (size_t)(k0 + 64) * np + k0; p.lda = np; p.sA = ms;
-        p.B = dinv + (size_t)kb * 4096; p.ldb = 64; p.sB = (int64_t)nb * 4096; p.tb = 1;
-        p.C = F + (size_t)(k0 + 64) * np + k0; p.ldc = np; p.sC = ms;
-        p.m = rem; p.n = 64; p.k = 64; p.batch = batch;
-        rc = lvae_gemm(p, st);
-        if (rc) return rc;
+        const double* P = F + (size_t)(k0 + 64) * np + k0;   // panel rows below the diagonal block (solved by k_diag_block)
         GemmDesc t;                                   // trailing: A22 -= P P^T on the lower tiles
-        t.A = p.C; t.lda = np; t.sA = ms;
-        t.B = p.C; t.ldb = np; t.sB = ms; t.tb = 1;
+        t.A = P; t.lda = np; t.sA = ms;
+        t.B = P; t.ldb = np; t.sB = ms; t.tb = 1;
         t.C = F + (size_t)(k0 + 64) * np + k0 + 64; t.ldc = np; t.sC = ms;
         t.m = rem; t.n = rem; t.k = 64; t.batch = batch;
         t.alpha = -1.0; t.beta = 1.0; t.flags = LVAE_GEMM_LOWER;
@@ -150,6 +221,16 @@ int lvae_gram_big(const double* X, double* Inv, int np, int batch, cudaStream_t 
     g.m = np; g.n = np; g.k = np; g.batch = batch;
     g.flags = LVAE_GEMM_LOWER | LVAE_GEMM_MIRROR;
     return lvae_gemm(g, st);
+}
+
+// SPD inverse: blocked Cholesky of F (in place), X = F^-1, Inv = X^T X (symmetric, identity padded like F).  T scratch.
+int lvae_spd_inverse_big(double* F, double* X, double* T, double* Inv, double* dinv, int np, int batch, int32_t* info,
+                         int info_mod, cudaStream_t st) {
+    int rc = lvae_potrf_big(F, np, batch, dinv, info, info_mod, st);
+    if (rc) return rc;
+    rc = lvae_trtri_big(F, dinv, X, T, np, batch, st);
+    if (rc) return rc;
+    return lvae_gram_big(X, Inv, np, batch, st);
 }
 
 int lvae_pad_in(double* dst, const double* src, int n, int np, int64_t sstride, int batch, double diag, int lower_only,

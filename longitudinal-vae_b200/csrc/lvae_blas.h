@@ -39,13 +39,17 @@ int64_t lvae_big_scratch_doubles(int np, int batch);
 
 // In-place blocked lower Cholesky of `batch` identity-padded np x np matrices (row stride np, matrix stride np*np).
 // The strict upper triangle is NOT cleared.  dinv: [batch][np/64][64*64] receives the inverses of the diagonal blocks of
-// the factor.  info_slot: device int32 set to 1 + (index % info_mod) of the first failing matrix.
+// the factor.  info_slot[index / info_mod] (info_mod > 0; else info_slot[0]) is set to 1 + (index % info_mod) of the first
+// failing matrix.
 int lvae_potrf_big(double* F, int np, int batch, double* dinv, int32_t* info_slot, int info_mod, cudaStream_t st);
 // X = F^-1 for the lower factor computed by lvae_potrf_big (X fully written, upper triangle zero); T: scratch batch*np*np.
 int lvae_trtri_big(const double* F, const double* dinv, double* X, double* T, int np, int batch, cudaStream_t st);
 // Inv = X^T X (symmetric, full).
 int lvae_gram_big(const double* X, double* Inv, int np, int batch, cudaStream_t st);
 
+// SPD inverse: blocked Cholesky of F in place, X = F^-1, Inv = X^T X (symmetric, full); T scratch.
+int lvae_spd_inverse_big(double* F, double* X, double* T, double* Inv, double* dinv, int np, int batch, int32_t* info,
+                         int info_mod, cudaStream_t st);
 int lvae_pad_in(double* dst, const double* src, int n, int np, int64_t sstride, int batch, double diag, int lower_only,
                 cudaStream_t st);
 int lvae_pad_out(double* dst, const double* src, int n, int np, int64_t dstride, int batch, int lower_only, cudaStream_t st);

@@ -47,7 +47,23 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.T3 = o; o += L * MM;
     w.a = o; o += L * M;
     w.logdet = o; o += L * 2;
-    w.v2 = (p->path == 0 || p->path == 2) && lvae_fused2_supported(p) ? 1 : 0;
+    w.big = (p->path != 1) && lvae_big_supported(p) ? 1 : 0;
+    w.MP = w.big ? (p->M <= 128 ? 128 : 256) : 0;
+    w.v2 = (((p->path == 0 || p->path == 2) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
+    w.nsplit = 1;
+    if (w.big) {
+        // CTAs per latent of the U/V and adjoint kernels: about two waves at 2 CTAs per SM
+        int n = (4 * 148 + p->L - 1) / p->L;
+        if (n > p->P_b) n = p->P_b > 0 ? p->P_b : 1;
+        w.nchunk = n < 1 ? 1 : n;
+        // k-splits of S = U^T U: enough (tile, latent, split) CTAs for two waves, at least 512 rows per split
+        const int tiles = w.MP == 128 ? 2 : 6;
+        int ns = (2 * 148 + tiles * p->L - 1) / (tiles * p->L);
+        const int cap = p->N_b / 512 > 0 ? p->N_b / 512 : 1;
+        if (ns > cap) ns = cap;
+        if (ns > 16) ns = 16;
+        w.nsplit = ns < 1 ? 1 : ns;
+    }
     w.TP = (p->T_max + 3) & ~3;
     if (w.TP < 4) w.TP = 4;
     w.gstride = (p->P_b + w.nchunk - 1) / w.nchunk + 1;
@@ -60,8 +76,30 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.gtab = o; o += w.v2 ? ((int64_t)w.nchunk * w.gstride * LVAE_F2_GT + 1) / 2 : 0;
     o += o & 1;
     w.gcount = o; o += w.v2 ? (w.nchunk + 1) / 2 : 0;
-    w.part = o; o += (int64_t)w.nchunk * L * w.stride;   // subject partials (S, ng1, da, A, hyp)
+    w.part = o; o += (int64_t)(w.big ? w.nsplit : w.nchunk) * L * w.stride;   // subject partials (S, ng1, da, A, hyp)
     w.ppart = o; o += (int64_t)w.nprep * L * (LVAE_NSCAL + w.nh);   // prep partials (scalars, hyp)
+    w.bpstride = 2 * (int64_t)w.MP + LVAE_NSCAL + w.nh;
+    if (w.big) {
+        const int64_t MP2 = (int64_t)w.MP * w.MP;
+        o += o & 1;
+        w.bF = o; o += 2 * L * MP2;
+        w.bX = o; o += 2 * L * MP2;
+        w.bInv = o; o += 2 * L * MP2;
+        w.bT = o; o += 2 * L * MP2;
+        w.bA0 = o; o += 2 * L * MP2;
+        w.bDinv = o; o += 2 * L * (w.MP / 64) * 4096;
+        w.bHp = o; o += L * MP2;
+        w.bWp = o; o += L * MP2;
+        w.bS = o; o += L * MP2;
+        w.bT1 = o; o += L * MP2;
+        w.bT2 = o; o += L * MP2;
+        w.bT3 = o; o += L * MP2;
+        w.bU = o; o += L * (int64_t)p->N_b * w.MP;
+        w.bV = o; o += L * (int64_t)p->N_b * w.MP;
+        w.bu = o; o += L * (int64_t)p->N_b;
+        o += o & 1;
+        w.bpart = o; o += (int64_t)w.nchunk * L * w.bpstride;
+    }
     w.total = o;
     return w;
 }
@@ -572,6 +610,11 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
     lvae_prof_begin(0, (cudaStream_t)stream);
+    if (w.big) {
+        rc = lvae_head_big_launch(p, sp, w, (cudaStream_t)stream);
+        lvae_prof_end(0, (cudaStream_t)stream);
+        return rc;
+    }
     if (p->M <= 64 && p->path != 1) {
         rc = lvae_head64_launch(p, sp, w, (cudaStream_t)stream);
         lvae_prof_end(0, (cudaStream_t)stream);
@@ -615,6 +658,16 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             LVAE_COUNT_LAUNCH();
         }
         lvae_prof_end(1, st);
+        if (w.big) {
+            lvae_prof_begin(2, st);
+            rc = lvae_subjects_big_launch(p, sp, w, st);
+            lvae_prof_end(2, st);
+            if (rc) return rc;
+            lvae_prof_begin(3, st);
+            rc = lvae_reduce_big_launch(p, w, st);
+            lvae_prof_end(3, st);
+            return rc;
+        }
         bool fused = w.v2 || (p->path == 2) || (p->path == 3) || (p->path == 0 && lvae_fused_supported(p));
         if (fused) {
             lvae_prof_begin(2, st);
@@ -641,6 +694,13 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         e = cudaMemsetAsync(p->workspace + w.ppart, 0, sizeof(double) * ((size_t)w.nprep * p->L * (LVAE_NSCAL + w.nh)), st);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
+        if (w.big) {
+            e = cudaMemsetAsync(p->workspace + w.part, 0, sizeof(double) * ((size_t)w.nsplit * p->L * w.stride), st);
+            if (e != cudaSuccess) return lvae_cuda_rc(e);
+            e = cudaMemsetAsync(p->workspace + w.bpart, 0, sizeof(double) * ((size_t)w.nchunk * p->L * w.bpstride), st);
+            if (e != cudaSuccess) return lvae_cuda_rc(e);
+            return lvae_reduce_big_launch(p, w, st);
+        }
     }
     lvae_prof_begin(3, st);
     k_reduce<<<dim3((unsigned)((w.stride + 255) / 256), p->L), 256, 0, st>>>(w, p->L, p->M, p->workspace, p->stats);
@@ -656,6 +716,11 @@ extern "C" int lvae_kld_tail_f64(const lvae_kld_problem_t* p, void* stream) {
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
     lvae_prof_begin(4, (cudaStream_t)stream);
+    if (w.big) {
+        rc = lvae_tail_big_launch(p, sp, w, (cudaStream_t)stream);
+        lvae_prof_end(4, (cudaStream_t)stream);
+        return rc;
+    }
     if (p->M <= 64 && p->path != 1) {
         rc = lvae_tail64_launch(p, sp, w, (cudaStream_t)stream);
         lvae_prof_end(4, (cudaStream_t)stream);
@@ -679,6 +744,7 @@ extern "C" int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream)
 }
 
 extern "C" int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p) { return lvae_layout(p).Hi; }
+extern "C" int64_t lvae_ng_workspace_doubles(int32_t L, int32_t M) { return M <= 64 ? 2 : lvae_ng_big_workspace(L, M); }
 
 extern "C" int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hinv,
                                 double lr, int32_t L, int32_t M, double* workspace, int32_t* info, void* stream) {
@@ -689,8 +755,7 @@ extern "C" int lvae_ng_step_f64(double* m, double* H, const double* grad_m, cons
         lvae_prof_end(5, (cudaStream_t)stream);
         return rc;
     }
-    k_ng_step<<<L, 256, 0, (cudaStream_t)stream>>>(m, H, grad_m, grad_H, lr, M, workspace, L, info);
+    const int rc = lvae_ng_big_launch(m, H, grad_m, grad_H, Hinv, lr, L, M, workspace, info, (cudaStream_t)stream);
     lvae_prof_end(5, (cudaStream_t)stream);
-    LVAE_COUNT_LAUNCH();
-    return lvae_cuda_rc(cudaGetLastError());
+    return rc;
 }

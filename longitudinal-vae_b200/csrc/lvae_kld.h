@@ -24,6 +24,15 @@ struct KldLayout {
     int TP, gstride, v2;
     int nh, nchunk;                     // nchunk: CTAs per latent of the subject pass
     int nprep;                          // partial rows per latent of the prep pass
+    // 64 < M <= 256: GEMM-based path (lvae_kld_big.cu, lvae_subjects_big.cu); matrices padded to MP = 128 or 256
+    int big, MP, nsplit;                // nsplit: k-splits of S = U^T U (rows of `part`); nchunk: CTAs per latent of k_uv / k_adj
+    int64_t bF, bX, bInv, bT, bA0;      // [2L, MP*MP]: factors, triangular inverses, explicit inverses (Kzz | H), scratch, originals
+    int64_t bDinv;                      // [2L, MP/64, 64*64] inverses of the diagonal blocks of the factors
+    int64_t bHp, bWp, bS, bT1, bT2, bT3;   // [L, MP*MP]: zero-padded H, W, S and products
+    int64_t bU, bV;                     // [L, N_b, MP]: U = L_p^-1 Kxz (later Y = V W), V = B_p^-1 Kxz
+    int64_t bu;                         // [L, N_b]: u = B_p^-1 r
+    int64_t bpart;                      // [nchunk, L, bpstride]: ng1 | da (MP each) | scalars | hyper-gradients
+    int64_t bpstride;
 };
 
 KldLayout lvae_layout(const lvae_kld_problem_t* p);
@@ -45,3 +54,13 @@ int lvae_ng64_launch(double* m, double* H, const double* grad_m, const double* g
 bool lvae_fused2_supported(const lvae_kld_problem_t* p);
 int lvae_plan_groups_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);
 int lvae_subjects_fused2_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+
+// 64 < M <= 256 (lvae_kld_big.cu / lvae_subjects_big.cu)
+bool lvae_big_supported(const lvae_kld_problem_t* p);
+int lvae_head_big_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+int lvae_tail_big_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+int lvae_subjects_big_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+int lvae_reduce_big_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);
+int64_t lvae_ng_big_workspace(int L, int M);
+int lvae_ng_big_launch(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hi, double lr, int L,
+                       int M, double* ws, int32_t* info, cudaStream_t st);

@@ -1,0 +1,489 @@
+// Per-subject pass of the GP-prior ELBO path for 64 < M <= 256 (at most 24 rows per subject), sm_100a FP64 tensor pipe.
+// With M this large the two M^2-sized contractions dominate (4 T M^2 of the ~4 T M^2 + 4 T^2 M flops per subject and
+// latent) and their arithmetic intensity against HBM is 2M/8 >= 16 flop/B, so U and V are materialised once in HBM and the
+// contractions run as large batched DMMA GEMMs (lvae_gemm.cu) instead of per-subject tiles:
+//   k_uv   per (latent, row group): Kxz from covariates, U = L_p^-1 Kxz, V = L_p^-T U (block-diagonal DMMA solves with
+//          the L_p^-1 rows of the prep kernel), r = Kxz a - mu, u = V a - B_p^-1 mu, d_mu, A, ng1 = sum V^T mu,
+//          da = sum V^T r; writes U, V [L, N_b, MP] and u [L, N_b]                  (elbo_functions.py:171,183,189-190,209-211)
+//   GEMM   S = U^T U (lower tiles, mirrored; k split over row ranges -> fixed-order partials)              (184)
+//   GEMM   Y = V W   (over U's storage)                                         (adjoint of S)
+//   k_adj  per (latent, row group): adjoint of Kxz = 2c u a^T + 2Y against d k_c / d theta; Q = Y V^T on the
+//          subject-diagonal tiles (each warp a k-slice, straight from global memory) and the adjoint of B_p
+//          = -(c u u^T + Q) against d K1 / d theta and its trace (noise)
+//   k_reduce_big  fixed-order sums of all partials into the statistics row (the only buffer exchanged between GPUs)
+#include "lvae_blas.h"
+#include "lvae_kld.h"
+
+namespace {
+
+constexpr int RG = LVAE_F2_ROWS;   // 24 rows per group
+constexpr int NMT = RG / 8;
+constexpr int LDL = 28;
+constexpr int GT = LVAE_F2_GT;
+constexpr int NCB = 8;             // components handled by the register accumulators
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void row_block(const int* mt_, int t, int R, int& lo, int& hi) {
+    lo = t; hi = t;
+    if (t < R) {
+        lo = 0; hi = 0;
+#pragma unroll
+        for (int s = 0; s < 5; ++s) { const int end = mt_[3 + s]; if (t >= end) lo = end; }
+#pragma unroll
+        for (int s = 4; s >= 0; --s) { const int end = mt_[3 + s]; if (t < end) hi = end; }
+    }
+}
+
+struct BigHyp {
+    double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
+};
+__device__ __forceinline__ void load_bighyp(BigHyp* h, const DevSpec& sp, const double* ls, const double* os, int L, int l) {
+    const int t = threadIdx.x;
+    if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; h->hil2[t] = 0.5 / (v * v); h->il3[t] = 1.0 / (v * v * v); }
+    if (t < sp.n0 + sp.n1) h->osc[t] = os[(size_t)t * L + l];
+    load_exp_table(h->etab);
+}
+
+__host__ __device__ inline size_t uv_doubles(int MP, int Q) {
+    return (size_t)RG * (MP + 4) + (size_t)RG * LDL + (size_t)MP * Q + (size_t)RG * Q + MP + 4 * RG + 16 * RG + 2 * RG / 2 + GT;
+}
+
+template <int NTW>
+__global__ void __launch_bounds__(256, 2)
+k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b,
+     const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ z, const double* __restrict__ ls,
+     const double* __restrict__ os, double c, double* __restrict__ d_mu, double* __restrict__ ws) {
+    constexpr int MP = 64 * NTW, LDM = MP + 4;
+    extern __shared__ double sm[];
+    __shared__ BigHyp hyp;
+    __shared__ double red[32];
+    const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, wl = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    double* const K = sm;                       // [RG][LDM] Kxz, then U in place (every warp only touches its own columns)
+    double* const Lg = K + RG * LDM;            // [RG][LDL] block-diagonal L^-1 of the group
+    double* const zs = Lg + RG * LDL;           // [MP][Q]
+    double* const xs = zs + MP * Q;             // [RG][Q]
+    double* const av = xs + RG * Q;             // [MP]
+    double* const mus = av + MP;                // [RG]
+    double* const bmus = mus + RG;
+    double* const rs = bmus + RG;
+    double* const us = rs + RG;
+    double* const rpart = us + RG;              // [8][RG]
+    double* const upart = rpart + 8 * RG;       // [8][RG]
+    int* const blo = reinterpret_cast<int*>(upart + 8 * RG);   // [RG]
+    int* const bhi = blo + RG;
+    int* const meta = bhi + RG;                 // [GT]
+
+    load_bighyp(&hyp, sp, ls, os, L, l);
+    for (int e = tid; e < MP * Q; e += 256) zs[e] = e < M * Q ? z[(size_t)l * M * Q + e] : 0.0;
+    for (int e = tid; e < MP; e += 256) av[e] = e < M ? ws[w.a + (size_t)l * M + e] : 0.0;
+    const int* gtab = reinterpret_cast<const int*>(ws + w.gtab) + (size_t)chunk * w.gstride * GT;
+    const int ngroups = reinterpret_cast<const int*>(ws + w.gcount)[chunk];
+    const double* Lrows = ws + w.Lrows + (size_t)l * N_b * w.TP;
+    const double* bmu_g = ws + w.bmu + (size_t)l * N_b;
+    double* const Ug = ws + w.bU + (size_t)l * N_b * MP;
+    double* const Vg = ws + w.bV + (size_t)l * N_b * MP;
+    double* const ug = ws + w.bu + (size_t)l * N_b;
+    const int colw = 8 * NTW * wl;              // first column of this warp
+
+    double ng1acc[NTW][2], daacc[NTW][2], accA = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) ng1acc[nt][0] = ng1acc[nt][1] = daacc[nt][0] = daacc[nt][1] = 0.0;
+
+    for (int gi = 0; gi < ngroups; ++gi) {
+        __syncthreads();
+        if (tid < GT) meta[tid] = gtab[(size_t)gi * GT + tid];
+        __syncthreads();
+        const int row0 = meta[0], R = meta[1];
+        const int R8 = (R + 7) & ~7, nmt = R8 >> 3;
+        if (tid < RG) {
+            int lo, hi;
+            row_block(meta, tid, R, lo, hi);
+            blo[tid] = lo; bhi[tid] = hi;
+            mus[tid] = tid < R ? mu[(size_t)(row0 + tid) * L + l] : 0.0;
+            bmus[tid] = tid < R ? bmu_g[row0 + tid] : 0.0;
+        }
+        for (int e = tid; e < RG * Q; e += 256) xs[e] = (e / Q) < R ? x[(size_t)row0 * Q + e] : 0.0;
+        __syncthreads();
+        for (int e = tid; e < RG * RG; e += 256) {
+            const int t = e / RG, k = e - t * RG, lo = blo[t];
+            Lg[t * LDL + k] = (k >= lo && k < bhi[t]) ? Lrows[(size_t)(row0 + t) * w.TP + (k - lo)] : 0.0;
+        }
+        // ---- Kxz from covariates (own columns) ; partial dots of r = Kxz a - mu -------------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            const bool rv = t < R;
+            double pr = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                const int j0 = colw + 8 * nt + 2 * q;
+                double kx0 = 0.0, kx1 = 0.0;
+                if (mt < nmt) {
+                    for (int cc = 0; cc < sp.n0; ++cc) {
+                        double f0, f1, d20, d21;
+                        comp_pair(sp, cc, xs + t * Q, zs + j0 * Q, zs + (j0 + 1) * Q, hyp.hil2, hyp.etab, f0, f1, d20, d21);
+                        kx0 += hyp.osc[cc] * f0;
+                        kx1 += hyp.osc[cc] * f1;
+                    }
+                    kx0 = (rv && j0 < M) ? kx0 : 0.0;
+                    kx1 = (rv && j0 + 1 < M) ? kx1 : 0.0;
+                }
+                *reinterpret_cast<double2*>(K + t * LDM + j0) = make_double2(kx0, kx1);
+                pr += kx0 * av[j0] + kx1 * av[j0 + 1];
+            }
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+            if (q == 0) rpart[wl * RG + t] = pr;
+        }
+        __syncthreads();
+        if (tid < RG) {
+            double s = -mus[tid];
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) s += rpart[ww * RG + tid];
+            rs[tid] = tid < R ? s : 0.0;
+        }
+        // ---- U = L^-1 Kxz (rows of a tile only see k <= row, inside their subject), in place over this warp's columns of K ----------
+        {
+            double u[NMT][NTW][2];
+#pragma unroll
+            for (int mt = 0; mt < NMT; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) u[mt][nt][0] = u[mt][nt][1] = 0.0;
+                if (mt < nmt) {
+                    const int klo = blo[8 * mt] >> 2;
+                    const int khi = min(2 * mt + 2, (bhi[min(8 * mt + 7, R - 1)] + 3) >> 2);
+                    for (int ks = klo; ks < khi; ++ks) {
+                        const double a = Lg[(8 * mt + g) * LDL + 4 * ks + q];
+#pragma unroll
+                        for (int nt = 0; nt < NTW; ++nt)
+                            dmma(u[mt][nt][0], u[mt][nt][1], a, K[(4 * ks + q) * LDM + colw + 8 * nt + g]);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int mt = 0; mt < NMT; ++mt) {
+                const int t = 8 * mt + g;
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) {
+                    const int j0 = colw + 8 * nt + 2 * q;
+                    *reinterpret_cast<double2*>(K + t * LDM + j0) = make_double2(u[mt][nt][0], u[mt][nt][1]);
+                    if (t < R) *reinterpret_cast<double2*>(Ug + (size_t)(row0 + t) * MP + j0) = make_double2(u[mt][nt][0], u[mt][nt][1]);
+                }
+            }
+        }
+        __syncthreads();          // rs and U visible
+        // ---- V = L^-T U ; ng1 += V^T mu ; da += V^T r ; partial dots of u = V a - B^-1 mu -----------------------------------------
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            double v[NTW][2];
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) v[nt][0] = v[nt][1] = 0.0;
+            if (mt < nmt) {
+                const int khi = (bhi[min(8 * mt + 7, R - 1)] + 3) >> 2;
+                for (int ks = 2 * mt; ks < khi; ++ks) {
+                    const double a = Lg[(4 * ks + q) * LDL + 8 * mt + g];
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt) dmma(v[nt][0], v[nt][1], a, K[(4 * ks + q) * LDM + colw + 8 * nt + g]);
+                }
+            }
+            const double tm = mus[t], tr = rs[t];
+            double pu = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                const int j0 = colw + 8 * nt + 2 * q;
+                if (t < R) *reinterpret_cast<double2*>(Vg + (size_t)(row0 + t) * MP + j0) = make_double2(v[nt][0], v[nt][1]);
+                ng1acc[nt][0] += v[nt][0] * tm; ng1acc[nt][1] += v[nt][1] * tm;
+                daacc[nt][0] += v[nt][0] * tr; daacc[nt][1] += v[nt][1] * tr;
+                pu += v[nt][0] * av[j0] + v[nt][1] * av[j0 + 1];
+            }
+            pu += __shfl_xor_sync(0xffffffffu, pu, 1);
+            pu += __shfl_xor_sync(0xffffffffu, pu, 2);
+            if (q == 0) upart[wl * RG + t] = pu;
+        }
+        __syncthreads();
+        if (tid < R) {
+            double s = -bmus[tid];
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) s += upart[ww * RG + tid];
+            ug[row0 + tid] = s;
+            d_mu[(size_t)(row0 + tid) * L + l] = -2.0 * c * s;
+            accA += rs[tid] * s;
+        }
+    }
+
+    // ---- CTA epilogue: fixed-order partials -------------------------------------------------------------------------------
+    double* bp = ws + w.bpart + ((size_t)chunk * L + l) * w.bpstride;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double a2 = ng1acc[nt][e], b2 = daacc[nt][e];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) { a2 += __shfl_xor_sync(0xffffffffu, a2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+            if (g == 0) { bp[colw + 8 * nt + 2 * q + e] = a2; bp[MP + colw + 8 * nt + 2 * q + e] = b2; }
+        }
+    }
+    const double a_ = block_sum(accA, red);
+    if (tid < LVAE_NSCAL) bp[2 * MP + tid] = (tid == SC_A) ? a_ : 0.0;
+}
+
+template <int NTW>
+__global__ void __launch_bounds__(256, 2)
+k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b,
+      const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls, const double* __restrict__ os,
+      double c, double* __restrict__ ws) {
+    constexpr int MP = 64 * NTW;
+    extern __shared__ double sm[];
+    __shared__ BigHyp hyp;
+    __shared__ double hypacc[8][2 * LVAE_MAXC + 2];
+    const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, wl = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int nh = hyp_count(sp), nc = sp.n0 + sp.n1;
+    double* const zs = sm;                      // [MP][Q]
+    double* const xs = zs + MP * Q;             // [RG][Q]
+    double* const av = xs + RG * Q;             // [MP]
+    double* const us = av + MP;                 // [RG]
+    int* const blo = reinterpret_cast<int*>(us + RG);
+    int* const meta = blo + RG;
+
+    load_bighyp(&hyp, sp, ls, os, L, l);
+    for (int e = tid; e < MP * Q; e += 256) zs[e] = e < M * Q ? z[(size_t)l * M * Q + e] : 0.0;
+    for (int e = tid; e < MP; e += 256) av[e] = e < M ? ws[w.a + (size_t)l * M + e] : 0.0;
+    const int* gtab = reinterpret_cast<const int*>(ws + w.gtab) + (size_t)chunk * w.gstride * GT;
+    const int ngroups = reinterpret_cast<const int*>(ws + w.gcount)[chunk];
+    const double* Yg = ws + w.bU + (size_t)l * N_b * MP;       // Y = V W was written over U
+    const double* Vg = ws + w.bV + (size_t)l * N_b * MP;
+    const double* ug = ws + w.bu + (size_t)l * N_b;
+    const int colw = 8 * NTW * wl;              // this warp's columns = its k-slice of Q = Y V^T
+
+    // hyper-gradient accumulators: one (outputscale, lengthscale) pair per component and warp, kept in shared memory and
+    // updated by lane 0 after a warp reduction -> the component loops stay rolled (small code, no register arrays)
+    for (int e = tid; e < 8 * (2 * LVAE_MAXC + 2); e += 256) (&hypacc[0][0])[e] = 0.0;
+    double gno = 0.0;
+
+    for (int gi = 0; gi < ngroups; ++gi) {
+        __syncthreads();
+        if (tid < GT) meta[tid] = gtab[(size_t)gi * GT + tid];
+        __syncthreads();
+        const int row0 = meta[0], R = meta[1];
+        const int R8 = (R + 7) & ~7, nmt = R8 >> 3;
+        if (tid < RG) {
+            int lo, hi;
+            row_block(meta, tid, R, lo, hi);
+            blo[tid] = lo;
+            us[tid] = tid < R ? ug[row0 + tid] : 0.0;
+        }
+        for (int e = tid; e < RG * Q; e += 256) xs[e] = (e / Q) < R ? x[(size_t)row0 * Q + e] : 0.0;
+        __syncthreads();
+        // ---- adjoint of Kxz = 2c u a^T + 2Y (own columns, registers) against d k_c / d theta of the K0 components ----------------------
+        double gb[NMT][NTW][2];
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            const bool rv = mt < nmt && t < R;
+            const double ut = 2.0 * c * us[t];
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                const int j0 = colw + 8 * nt + 2 * q;
+                double2 y = make_double2(0.0, 0.0);
+                if (rv) y = *reinterpret_cast<const double2*>(Yg + (size_t)(row0 + t) * MP + j0);
+                gb[mt][nt][0] = (rv && j0 < M) ? ut * av[j0] + 2.0 * y.x : 0.0;
+                gb[mt][nt][1] = (rv && j0 + 1 < M) ? ut * av[j0 + 1] + 2.0 * y.y : 0.0;
+            }
+        }
+        for (int cc = 0; cc < sp.n0; ++cc) {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < NMT; ++mt) {
+                if (mt < nmt) {
+                    const int t = 8 * mt + g;
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt) {
+                        const int j0 = colw + 8 * nt + 2 * q;
+                        double f0, f1, d20, d21;
+                        comp_pair(sp, cc, xs + t * Q, zs + j0 * Q, zs + (j0 + 1) * Q, hyp.hil2, hyp.etab, f0, f1, d20, d21);
+                        const double w0 = gb[mt][nt][0] * f0, w1 = gb[mt][nt][1] * f1;
+                        s1 += w0 + w1;
+                        s2 += w0 * d20 + w1 * d21;
+                    }
+                }
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) {
+                hypacc[wl][sp.n_ls + cc] += s1;
+                if (sp.rbf_dim[cc] >= 0) hypacc[wl][sp.ls_idx[cc]] += s2 * hyp.osc[cc] * hyp.il3[sp.ls_idx[cc]];
+            }
+        }
+        // ---- Q = Y V^T over this warp's k-slice, subject-diagonal upper tiles ; adjoint of B_p = -(c u u^T + Q) ---------------------
+        double qa[6][2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) qa[i][0] = qa[i][1] = 0.0;
+#pragma unroll 4
+        for (int ks = 0; ks < 2 * NTW; ++ks) {
+            const int kk = colw + 4 * ks + q;
+            double ya[NMT], vb[NMT];
+#pragma unroll
+            for (int mt = 0; mt < NMT; ++mt) {
+                const int t = 8 * mt + g;
+                const bool ok = t < R;
+                ya[mt] = ok ? Yg[(size_t)(row0 + t) * MP + kk] : 0.0;
+                vb[mt] = ok ? Vg[(size_t)(row0 + t) * MP + kk] : 0.0;
+            }
+            dmma(qa[0][0], qa[0][1], ya[0], vb[0]);
+            dmma(qa[1][0], qa[1][1], ya[0], vb[1]);
+            dmma(qa[2][0], qa[2][1], ya[1], vb[1]);
+            dmma(qa[3][0], qa[3][1], ya[0], vb[2]);
+            dmma(qa[4][0], qa[4][1], ya[1], vb[2]);
+            dmma(qa[5][0], qa[5][1], ya[2], vb[2]);
+        }
+        // gB of this lane's entries (tile tl = (i <= jt), entries (8i + g, 8jt + 2q + e)); zero outside the subject blocks
+#pragma unroll
+        for (int tl = 0; tl < 6; ++tl) {
+            const int jt = tl < 1 ? 0 : (tl < 3 ? 1 : 2);
+            const int i = tl - (jt * (jt + 1)) / 2;
+            const int t = 8 * i + g;
+            const double wgt = jt > i ? -2.0 : -1.0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int t2 = 8 * jt + 2 * q + e;
+                const bool on = jt < nmt && t < R && t2 < R && blo[t] == blo[t2];
+                const double gB = on ? wgt * ((wl == 0 ? c * us[t] * us[t2] : 0.0) + qa[tl][e]) : 0.0;
+                qa[tl][e] = gB;
+                if (t == t2) gno += gB;
+            }
+        }
+        for (int cc = sp.n0; cc < nc; ++cc) {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int tl = 0; tl < 6; ++tl) {
+                const int jt = tl < 1 ? 0 : (tl < 3 ? 1 : 2);
+                const int i = tl - (jt * (jt + 1)) / 2;
+                if (jt < nmt) {
+                    const int t = 8 * i + g;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int t2 = 8 * jt + 2 * q + e;
+                        double d2;
+                        const double f = comp_one(sp, cc, xs + t * Q, xs + t2 * Q, hyp.hil2, hyp.etab, d2);
+                        const double w_ = qa[tl][e] * f;
+                        s1 += w_;
+                        s2 += w_ * d2;
+                    }
+                }
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) {
+                hypacc[wl][sp.n_ls + cc] += s1;
+                if (sp.rbf_dim[cc] >= 0) hypacc[wl][sp.ls_idx[cc]] += s2 * hyp.osc[cc] * hyp.il3[sp.ls_idx[cc]];
+            }
+        }
+    }
+
+    // ---- CTA epilogue: hyper-gradient partials of this CTA, fixed order ------------------------------------------------------------
+    {
+        const double n_ = warp_sum(gno);
+        if (lane == 0) hypacc[wl][nh - 1] += n_;
+    }
+    __syncthreads();
+    double* bp = ws + w.bpart + ((size_t)chunk * L + l) * w.bpstride + 2 * MP + LVAE_NSCAL;
+    if (tid < nh) {
+        double s = 0.0;
+        for (int ww = 0; ww < 8; ++ww) s += hypacc[ww][tid];
+        bp[tid] = s;
+    }
+}
+
+// stats[l][k] = fixed-order sum of the S partials (k < M^2) or of the k_uv / k_adj / prep partials (vectors, scalars, hyper-gradients)
+__global__ void __launch_bounds__(256) k_reduce_big(KldLayout w, int L, int M, const double* __restrict__ ws,
+                                                    double* __restrict__ stats) {
+    const int l = blockIdx.y;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= w.stride) return;
+    const int64_t MM = (int64_t)M * M;
+    double s = 0.0;
+    if (k < MM) {
+        for (int ch = 0; ch < w.nsplit; ++ch) s += ws[w.part + ((size_t)ch * L + l) * w.stride + k];
+    } else {
+        const int64_t kv = k - MM;                          // ng1 [M] | da [M] | scalars | hyp
+        const int64_t src = kv < M ? kv : (kv < 2 * M ? w.MP + (kv - M) : 2 * (int64_t)w.MP + (kv - 2 * M));
+        for (int ch = 0; ch < w.nchunk; ++ch) s += ws[w.bpart + ((size_t)ch * L + l) * w.bpstride + src];
+        const int64_t ks = k - stats_off_scal(M);
+        if (ks >= 0) {
+            for (int ch = 0; ch < w.nprep; ++ch) s += ws[w.ppart + ((size_t)ch * L + l) * (LVAE_NSCAL + w.nh) + ks];
+        }
+    }
+    stats[(size_t)l * w.stride + k] = s;
+}
+
+template <int NTW>
+int launch_uv(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    const size_t smem = sizeof(double) * uv_doubles(64 * NTW, p->Q);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_uv<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return lvae_cuda_rc(e);
+        attr = smem;
+    }
+    k_uv<NTW><<<dim3(w.nchunk, p->L), 256, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, p->x, p->mu, p->z, p->lengthscale,
+                                                        p->outputscale, 0.5 * p->scale, p->d_mu, p->workspace);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+template <int NTW>
+int launch_adj(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    const int MP = 64 * NTW;
+    const size_t smem = sizeof(double) * ((size_t)MP * p->Q + (size_t)RG * p->Q + MP + RG + RG / 2 + GT);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_adj<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return lvae_cuda_rc(e);
+        attr = smem;
+    }
+    k_adj<NTW><<<dim3(w.nchunk, p->L), 256, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, p->x, p->z, p->lengthscale,
+                                                         p->outputscale, 0.5 * p->scale, p->workspace);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
+}  // namespace
+
+int lvae_subjects_big_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    const int L = p->L, M = p->M, MP = w.MP, N_b = p->N_b;
+    double* ws = p->workspace;
+    int rc = MP == 128 ? launch_uv<2>(p, sp, w, st) : launch_uv<4>(p, sp, w, st);
+    if (rc) return rc;
+    GemmDesc s;                                   // S partials: part[split][l] = U_l[rows of the split]^T U_l[same rows]
+    int kchunk = (N_b + w.nsplit - 1) / w.nsplit;
+    kchunk = (kchunk + 15) & ~15;
+    s.A = ws + w.bU; s.lda = MP; s.sA = (int64_t)N_b * MP; s.ta = 1;
+    s.B = ws + w.bU; s.ldb = MP; s.sB = (int64_t)N_b * MP;
+    s.C = ws + w.part; s.ldc = M; s.sC = w.stride;
+    s.m = M; s.n = M; s.k = N_b; s.batch = L;
+    s.ksplit = w.nsplit; s.kchunk = kchunk;
+    s.kA = (int64_t)kchunk * MP; s.kB = (int64_t)kchunk * MP; s.kC = (int64_t)L * w.stride;
+    s.flags = LVAE_GEMM_LOWER | LVAE_GEMM_MIRROR;
+    rc = lvae_gemm(s, st);
+    if (rc) return rc;
+    GemmDesc y;                                   // Y = V W, written over U
+    y.A = ws + w.bV; y.lda = MP; y.sA = (int64_t)N_b * MP;
+    y.B = ws + w.bWp; y.ldb = MP; y.sB = (int64_t)MP * MP;
+    y.C = ws + w.bU; y.ldc = MP; y.sC = (int64_t)N_b * MP;
+    y.m = N_b; y.n = MP; y.k = MP; y.batch = L;
+    rc = lvae_gemm(y, st);
+    if (rc) return rc;
+    return MP == 128 ? launch_adj<2>(p, sp, w, st) : launch_adj<4>(p, sp, w, st);
+}
+
+int lvae_reduce_big_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st) {
+    k_reduce_big<<<dim3((unsigned)((w.stride + 255) / 256), p->L), 256, 0, st>>>(w, p->L, p->M, p->workspace, p->stats);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}

@@ -158,7 +158,7 @@ def ng_step(m, H, grad_m, grad_H, lr, Hinv=None):
     L, M = H.shape[0], H.shape[-1]
     m2, H2 = _c(m).clone(), _c(H).clone()
     gm, gH = _c(grad_m), _c(grad_H)
-    ws = torch.empty(4 * L * M * M if M > 64 else 1, dtype=F64, device=H.device)
+    ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=F64, device=H.device)
     info = torch.zeros(4, dtype=torch.int32, device=H.device)
     hi = _c(Hinv) if Hinv is not None else None
     with torch.cuda.device(H.device):

@@ -18,12 +18,15 @@ WELL_CONDITIONED = ("cfg2_noNG", "cfg4_ragged", "missing_mask")
 TOL = 1e-6
 
 
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 0])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_bound_and_gradients_vs_reference_golden(name, path):
+    """path 1: generic kernels; 2: fused DMMA subject kernel (M <= 64); 0: auto, which for M > 64 is the GEMM-based path."""
     g = load_golden(name)
     if path == 2 and g["H"].shape[-1] > 64:
         pytest.skip("fused DMMA kernel covers M <= 64")
+    if path == 0 and g["H"].shape[-1] <= 64:
+        pytest.skip("auto == fused for M <= 64 (covered by path 2)")
     out = run_cuda_case(g, path=path)
     assert abs(out["kld"] - float(g["kld"])) <= TOL * abs(float(g["kld"]))
     assert rel(out["d_mu"], g["d_mu"]) < TOL
@@ -205,6 +208,46 @@ def test_fresh_seeded_inputs_vs_oracle(cfg, P, L, M):
     assert abs(out[0].item() - ref[0].item()) <= TOL * abs(ref[0].item())
     assert rel(out[1], ref[1]) < TOL and rel(out[2], ref[2]) < TOL
     assert rel(mu.grad, mu_o.grad) < TOL
+
+
+@pytest.mark.parametrize("cfg,P,L,M,ng", [("cfg5", 30, 3, 128, False), ("cfg3", 25, 2, 200, False), ("cfg3", 32, 2, 256, True),
+                                          ("cfg5", 10, 5, 72, True)])
+def test_big_path_matches_generic_kernels(cfg, P, L, M, ng):
+    """64 < M <= 256: the GEMM-based path (auto) against the generic kernels (path 1, golden-checked above), all outputs,
+    both natural_gradient modes, M that is not a multiple of the 64-wide blocks."""
+    from lvae_b200 import synth
+    b = synth.make_batch(cfg, P=P, L=L, M=M)
+    n_ls = 4
+    ls, os_, noise = synth.perturbed_hypers(n_ls, 5, L, seed=11)
+    g = dict(lists=b.lists, lengthscale=ls.numpy(), outputscale=os_.numpy(), noise=noise.numpy(), mu=b.mu.numpy(),
+             log_v=b.log_v.numpy(), m=b.m.numpy(), H=b.H.numpy(), x=b.x.numpy(), z=b.z.numpy(), offsets=b.offsets,
+             natural_gradient=ng, ragged=False, P_tot=3 * P, T=b.T, eps=1e-6)
+    a = run_cuda_case(g, path=0)
+    r = run_cuda_case(g, path=1)
+    assert abs(a["kld"] - r["kld"]) <= 1e-7 * abs(r["kld"])
+    for k in r:
+        if k != "kld":
+            assert rel(a[k], r[k]) < TOL, k
+
+
+def test_natural_gradient_step_big_m():
+    """training.py:129-135 for M > 64 (blocked Cholesky / inverse on DMMA GEMMs) vs the oracle, with and without the
+    head's H^-1."""
+    import lvae_oracle as orc
+    from lvae_b200 import ops
+    torch.manual_seed(5)
+    L, M = 3, 150
+    A = torch.randn(L, M, M, dtype=torch.float64) / 10
+    H = A @ A.transpose(1, 2) + 0.1 * torch.eye(M, dtype=torch.float64)
+    m = torch.randn(L, M, 1, dtype=torch.float64)
+    gm = torch.randn(L, M, 1, dtype=torch.float64)
+    B = torch.randn(L, M, M, dtype=torch.float64) / 20
+    gH = B @ B.transpose(1, 2)
+    m_ref, H_ref = orc.ng_step(m, H, gm, gH, 0.05)
+    m1, H1, info = ops.ng_step(m.cuda(), H.cuda(), gm.cuda(), gH.cuda(), 0.05)
+    assert rel(m1, m_ref) < 1e-9 and rel(H1, H_ref) < 1e-9 and int(info.abs().sum()) == 0
+    m2, H2, _ = ops.ng_step(m.cuda(), H.cuda(), gm.cuda(), gH.cuda(), 0.05, Hinv=torch.linalg.inv(H).cuda())
+    assert rel(m2, m_ref) < 1e-9 and rel(H2, H_ref) < 1e-9
 
 
 def test_device_exp_accuracy():
