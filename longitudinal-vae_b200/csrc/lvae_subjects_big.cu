@@ -38,18 +38,161 @@ __device__ __forceinline__ void row_block(const int* mt_, int t, int R, int& lo,
     }
 }
 
-struct BigHyp {
-    double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
+// Per-latent component table in shared memory + covariates GATHERED per component (slot 0: the column of the
+// squared-exponential factor, slots 1..3: the columns of the categorical / binary factors), so the evaluation loops only
+// see base + constant addresses and warp-uniform branches:  XC[c][slot][row] for the rows of a group, ZC[c][slot][column]
+// for the inducing points.
+constexpr int CS = 4;
+struct CompTab {
+    double negh[LVAE_MAXC];      // -1 / (2 l^2) of the component's SE factor
+    double osc[LVAE_MAXC];
+    double lsw[LVAE_MAXC];       // outputscale / l^3: weight of sum(gbar f d^2) in d/d lengthscale
+    double etab[LVAE_EXP_TBL];
+    int nmask[LVAE_MAXC], rbf[LVAE_MAXC], lsidx[LVAE_MAXC], mtype[LVAE_MAXC][LVAE_MAX_MASKS];
+    int dim[LVAE_MAXC][CS];      // covariate column of every slot (-1: unused)
 };
-__device__ __forceinline__ void load_bighyp(BigHyp* h, const DevSpec& sp, const double* ls, const double* os, int L, int l) {
-    const int t = threadIdx.x;
-    if (t < sp.n_ls) { const double v = ls[(size_t)t * L + l]; h->hil2[t] = 0.5 / (v * v); h->il3[t] = 1.0 / (v * v * v); }
-    if (t < sp.n0 + sp.n1) h->osc[t] = os[(size_t)t * L + l];
-    load_exp_table(h->etab);
+__device__ __forceinline__ void load_comptab(CompTab* ct, const DevSpec& sp, const double* ls, const double* os, int L, int l) {
+    const int t = threadIdx.x, nc = sp.n0 + sp.n1;
+    if (t < nc) {
+        const int li = sp.ls_idx[t], rd = sp.rbf_dim[t];
+        double negh = 0.0, lsw = 0.0;
+        const double o = os[(size_t)t * L + l];
+        if (rd >= 0) { const double v = ls[(size_t)li * L + l]; negh = -0.5 / (v * v); lsw = o / (v * v * v); }
+        ct->negh[t] = negh; ct->osc[t] = o; ct->lsw[t] = lsw;
+        ct->nmask[t] = sp.n_mask[t]; ct->rbf[t] = rd >= 0; ct->lsidx[t] = li;
+        ct->dim[t][0] = rd;
+        for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
+            ct->mtype[t][i] = sp.mask_type[t][i];
+            ct->dim[t][1 + i] = i < sp.n_mask[t] ? sp.mask_dim[t][i] : -1;
+        }
+    }
+    load_exp_table(ct->etab);
+}
+// gather the covariates of `n` rows (row-major [n][Q] at `src`, rows >= nvalid read as zero) into dst[c][slot][ld]
+__device__ __forceinline__ void gather_cov(const CompTab& ct, int c_begin, int c_end, const double* __restrict__ src, int Q,
+                                           int n, int nvalid, int ld, double* __restrict__ dst) {
+    const int total = (c_end - c_begin) * CS * n;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int r = e % n, sl = (e / n) % CS, c = c_begin + e / (n * CS);
+        const int dim = ct.dim[c][sl];
+        dst[((size_t)(c - c_begin) * CS + sl) * ld + r] = (dim >= 0 && r < nvalid) ? src[(size_t)r * Q + dim] : 0.0;
+    }
+}
+// Un-scaled values of ONE component on this lane's entries of a row group: rows 8*mt + g (mt < nmt), column pairs
+// (j0, j0 + 1), j0 = colw + 8*nt + 2q (nt < NTW).  NM (number of categorical / binary factors) and RBF are compile-time,
+// so the body is straight-line: per factor one FMA + compare per column (cat: a - b == 0, bin: a + b == 2, both written
+// as fma(sgn, b, a) == tgt, exactly rounded like the reference's subtraction / addition), per SE factor one exp per column.
+// `fn(mt, nt, f0, f1, d20, d21)` consumes the values.  Row / column validity is the caller's business.
+template <int NM, bool RBF, int NTW, class Fn>
+__device__ __forceinline__ void eval_block(const CompTab& ct, int c, const double* __restrict__ XCc, const double* __restrict__ ZCc,
+                                           int ldz, int nmt, int g, int q, int colw, Fn&& fn) {
+    double sgn[NM > 0 ? NM : 1], tgt[NM > 0 ? NM : 1];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+        const bool cat = ct.mtype[c][i] == LVAE_CAT;
+        sgn[i] = cat ? -1.0 : 1.0;
+        tgt[i] = cat ? 0.0 : 2.0;
+    }
+    const double h = ct.negh[c];
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+        if (mt < nmt) {
+            const int t = 8 * mt + g;
+            double am[NM > 0 ? NM : 1];
+#pragma unroll
+            for (int i = 0; i < NM; ++i) am[i] = XCc[(1 + i) * RG + t];
+            const double ar = RBF ? XCc[t] : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                const int j0 = colw + 8 * nt + 2 * q;
+                bool on0 = true, on1 = true;
+#pragma unroll
+                for (int i = 0; i < NM; ++i) {
+                    const double2 b = *reinterpret_cast<const double2*>(ZCc + (1 + i) * ldz + j0);
+                    on0 = on0 && (fma(sgn[i], b.x, am[i]) == tgt[i]);
+                    on1 = on1 && (fma(sgn[i], b.y, am[i]) == tgt[i]);
+                }
+                double e0 = 1.0, e1 = 1.0, d20 = 0.0, d21 = 0.0;
+                if (RBF) {
+                    const double2 b = *reinterpret_cast<const double2*>(ZCc + j0);
+                    const double t0 = ar - b.x, t1 = ar - b.y;
+                    d20 = t0 * t0; d21 = t1 * t1;
+                    e0 = exp_neg(d20 * h, ct.etab);
+                    e1 = exp_neg(d21 * h, ct.etab);
+                }
+                fn(mt, nt, on0 ? e0 : 0.0, on1 ? e1 : 0.0, d20, d21);
+            }
+        }
+    }
+}
+// generic shape (2-3 factors): run-time factor loop
+template <int NTW, class Fn>
+__device__ __forceinline__ void eval_generic(const CompTab& ct, int c, const double* __restrict__ XCc, const double* __restrict__ ZCc,
+                                          int ldz, int nmt, int g, int q, int colw, Fn& fn) {
+    const int nm = ct.nmask[c];
+    const double h = ct.negh[c];
+    const bool rbf = ct.rbf[c] != 0;
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+        if (mt >= nmt) continue;
+        const int t = 8 * mt + g;
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+            const int j0 = colw + 8 * nt + 2 * q;
+            bool on0 = true, on1 = true;
+            for (int i = 0; i < nm; ++i) {
+                const double a = XCc[(1 + i) * RG + t];
+                const double2 b = *reinterpret_cast<const double2*>(ZCc + (1 + i) * ldz + j0);
+                if (ct.mtype[c][i] == LVAE_CAT) { on0 = on0 && (a - b.x == 0.0); on1 = on1 && (a - b.y == 0.0); }
+                else { on0 = on0 && (a + b.x == 2.0); on1 = on1 && (a + b.y == 2.0); }
+            }
+            double e0 = 1.0, e1 = 1.0, d20 = 0.0, d21 = 0.0;
+            if (rbf) {
+                const double a = XCc[t];
+                const double2 b = *reinterpret_cast<const double2*>(ZCc + j0);
+                const double t0 = a - b.x, t1 = a - b.y;
+                d20 = t0 * t0; d21 = t1 * t1;
+                e0 = exp_neg(d20 * h, ct.etab);
+                e1 = exp_neg(d21 * h, ct.etab);
+            }
+            fn(mt, nt, on0 ? e0 : 0.0, on1 ? e1 : 0.0, d20, d21);
+        }
+    }
+}
+// warp-uniform dispatch on the component's shape: straight-line code for the shapes kernel_gen.py produces without
+// missing-value masks (SE, cat/bin x SE, cat/bin), a run-time factor loop for 2-3 factors
+template <int NTW, class Fn>
+__device__ __forceinline__ void eval_component(const CompTab& ct, int c, const double* __restrict__ XCc,
+                                               const double* __restrict__ ZCc, int ldz, int nmt, int g, int q, int colw, Fn&& fn) {
+    const int nm = ct.nmask[c];
+    const bool rbf = ct.rbf[c] != 0;
+    if (nm == 0) eval_block<0, true, NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
+    else if (nm == 1 && rbf) eval_block<1, true, NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
+    else if (nm == 1) eval_block<1, false, NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
+    else eval_generic<NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
+}
+// single entry, both sides from the gathered row covariates (K1 components on (X_p, X_p))
+__device__ __forceinline__ double eval_rows(const CompTab& ct, int c, const double* __restrict__ XCc, int ldx, int t, int t2,
+                                            double& d2) {
+    bool on = true;
+    const int nm = ct.nmask[c];
+    for (int i = 0; i < nm; ++i) {
+        const double a = XCc[(1 + i) * ldx + t], b = XCc[(1 + i) * ldx + t2];
+        on = on && ((ct.mtype[c][i] == LVAE_CAT) ? (a - b == 0.0) : (a + b == 2.0));
+    }
+    double e = 1.0;
+    d2 = 0.0;
+    if (ct.rbf[c]) {
+        const double dd = XCc[t] - XCc[t2];
+        d2 = dd * dd;
+        e = exp_neg(d2 * ct.negh[c], ct.etab);
+    }
+    return on ? e : 0.0;
 }
 
 __host__ __device__ inline size_t uv_doubles(int MP, int Q) {
-    return (size_t)RG * (MP + 4) + (size_t)RG * LDL + (size_t)MP * Q + (size_t)RG * Q + MP + 4 * RG + 16 * RG + 2 * RG / 2 + GT;
+    (void)Q;
+    return (size_t)RG * (MP + 4) + (size_t)RG * LDL + (size_t)4 * CS * MP + (size_t)4 * CS * RG + MP + 4 * RG + 16 * RG + 2 * RG / 2 + GT;
 }
 
 template <int NTW>
@@ -59,14 +202,14 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
      const double* __restrict__ os, double c, double* __restrict__ d_mu, double* __restrict__ ws) {
     constexpr int MP = 64 * NTW, LDM = MP + 4;
     extern __shared__ double sm[];
-    __shared__ BigHyp hyp;
+    __shared__ CompTab ct;
     __shared__ double red[32];
     const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, wl = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     double* const K = sm;                       // [RG][LDM] Kxz, then U in place (every warp only touches its own columns)
     double* const Lg = K + RG * LDM;            // [RG][LDL] block-diagonal L^-1 of the group
-    double* const zs = Lg + RG * LDL;           // [MP][Q]
-    double* const xs = zs + MP * Q;             // [RG][Q]
-    double* const av = xs + RG * Q;             // [MP]
+    double* const ZC = Lg + RG * LDL;           // [4][CS][MP] gathered inducing covariates of the K0 components
+    double* const XC = ZC + 4 * CS * MP;        // [4][CS][RG] gathered row covariates
+    double* const av = XC + 4 * CS * RG;        // [MP]
     double* const mus = av + MP;                // [RG]
     double* const bmus = mus + RG;
     double* const rs = bmus + RG;
@@ -77,8 +220,9 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
     int* const bhi = blo + RG;
     int* const meta = bhi + RG;                 // [GT]
 
-    load_bighyp(&hyp, sp, ls, os, L, l);
-    for (int e = tid; e < MP * Q; e += 256) zs[e] = e < M * Q ? z[(size_t)l * M * Q + e] : 0.0;
+    load_comptab(&ct, sp, ls, os, L, l);
+    __syncthreads();
+    gather_cov(ct, 0, sp.n0, z + (size_t)l * M * Q, Q, MP, M, MP, ZC);
     for (int e = tid; e < MP; e += 256) av[e] = e < M ? ws[w.a + (size_t)l * M + e] : 0.0;
     const int* gtab = reinterpret_cast<const int*>(ws + w.gtab) + (size_t)chunk * w.gstride * GT;
     const int ngroups = reinterpret_cast<const int*>(ws + w.gcount)[chunk];
@@ -106,38 +250,42 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
             mus[tid] = tid < R ? mu[(size_t)(row0 + tid) * L + l] : 0.0;
             bmus[tid] = tid < R ? bmu_g[row0 + tid] : 0.0;
         }
-        for (int e = tid; e < RG * Q; e += 256) xs[e] = (e / Q) < R ? x[(size_t)row0 * Q + e] : 0.0;
+        gather_cov(ct, 0, sp.n0, x + (size_t)row0 * Q, Q, RG, R, RG, XC);
         __syncthreads();
         for (int e = tid; e < RG * RG; e += 256) {
             const int t = e / RG, k = e - t * RG, lo = blo[t];
             Lg[t * LDL + k] = (k >= lo && k < bhi[t]) ? Lrows[(size_t)(row0 + t) * w.TP + (k - lo)] : 0.0;
         }
-        // ---- Kxz from covariates (own columns) ; partial dots of r = Kxz a - mu -------------------------------------------
+        // ---- Kxz from the gathered covariates (own columns) ; partial dots of r = Kxz a - mu ---------------------------------
+        {
+            double kx[NMT][NTW][2];
 #pragma unroll
-        for (int mt = 0; mt < NMT; ++mt) {
-            const int t = 8 * mt + g;
-            const bool rv = t < R;
-            double pr = 0.0;
+            for (int mt = 0; mt < NMT; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                const int j0 = colw + 8 * nt + 2 * q;
-                double kx0 = 0.0, kx1 = 0.0;
-                if (mt < nmt) {
-                    for (int cc = 0; cc < sp.n0; ++cc) {
-                        double f0, f1, d20, d21;
-                        comp_pair(sp, cc, xs + t * Q, zs + j0 * Q, zs + (j0 + 1) * Q, hyp.hil2, hyp.etab, f0, f1, d20, d21);
-                        kx0 += hyp.osc[cc] * f0;
-                        kx1 += hyp.osc[cc] * f1;
-                    }
-                    kx0 = (rv && j0 < M) ? kx0 : 0.0;
-                    kx1 = (rv && j0 + 1 < M) ? kx1 : 0.0;
-                }
-                *reinterpret_cast<double2*>(K + t * LDM + j0) = make_double2(kx0, kx1);
-                pr += kx0 * av[j0] + kx1 * av[j0 + 1];
+                for (int nt = 0; nt < NTW; ++nt) kx[mt][nt][0] = kx[mt][nt][1] = 0.0;
+            for (int cc = 0; cc < sp.n0; ++cc) {
+                const double o = ct.osc[cc];
+                eval_component<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, nmt, g, q, colw,
+                                    [&](int mt, int nt, double f0, double f1, double, double) {
+                                        kx[mt][nt][0] += o * f0;
+                                        kx[mt][nt][1] += o * f1;
+                                    });
             }
-            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-            if (q == 0) rpart[wl * RG + t] = pr;
+#pragma unroll
+            for (int mt = 0; mt < NMT; ++mt) {
+                const int t = 8 * mt + g;
+                double pr = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) {
+                    const int j0 = colw + 8 * nt + 2 * q;
+                    const double k0_ = (t < R && j0 < M) ? kx[mt][nt][0] : 0.0, k1_ = (t < R && j0 + 1 < M) ? kx[mt][nt][1] : 0.0;
+                    *reinterpret_cast<double2*>(K + t * LDM + j0) = make_double2(k0_, k1_);
+                    pr += k0_ * av[j0] + k1_ * av[j0 + 1];
+                }
+                pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+                pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+                if (q == 0) rpart[wl * RG + t] = pr;
+            }
         }
         __syncthreads();
         if (tid < RG) {
@@ -240,19 +388,21 @@ k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, i
       double c, double* __restrict__ ws) {
     constexpr int MP = 64 * NTW;
     extern __shared__ double sm[];
-    __shared__ BigHyp hyp;
+    __shared__ CompTab ct;
     __shared__ double hypacc[8][2 * LVAE_MAXC + 2];
     const int chunk = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, wl = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int nh = hyp_count(sp), nc = sp.n0 + sp.n1;
-    double* const zs = sm;                      // [MP][Q]
-    double* const xs = zs + MP * Q;             // [RG][Q]
-    double* const av = xs + RG * Q;             // [MP]
+    double* const ZC = sm;                      // [4][CS][MP] gathered inducing covariates of the K0 components
+    double* const XC = ZC + 4 * CS * MP;        // [NCB][CS][RG] gathered row covariates of all components
+    double* const av = XC + NCB * CS * RG;      // [MP]
     double* const us = av + MP;                 // [RG]
-    int* const blo = reinterpret_cast<int*>(us + RG);
+    double* const qred = us + RG;               // [8 warps][6 tiles][32 lanes][2] partial Q of the warps' k-slices
+    int* const blo = reinterpret_cast<int*>(qred + 8 * 6 * 64);
     int* const meta = blo + RG;
 
-    load_bighyp(&hyp, sp, ls, os, L, l);
-    for (int e = tid; e < MP * Q; e += 256) zs[e] = e < M * Q ? z[(size_t)l * M * Q + e] : 0.0;
+    load_comptab(&ct, sp, ls, os, L, l);
+    __syncthreads();
+    gather_cov(ct, 0, sp.n0, z + (size_t)l * M * Q, Q, MP, M, MP, ZC);
     for (int e = tid; e < MP; e += 256) av[e] = e < M ? ws[w.a + (size_t)l * M + e] : 0.0;
     const int* gtab = reinterpret_cast<const int*>(ws + w.gtab) + (size_t)chunk * w.gstride * GT;
     const int ngroups = reinterpret_cast<const int*>(ws + w.gcount)[chunk];
@@ -278,7 +428,7 @@ k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, i
             blo[tid] = lo;
             us[tid] = tid < R ? ug[row0 + tid] : 0.0;
         }
-        for (int e = tid; e < RG * Q; e += 256) xs[e] = (e / Q) < R ? x[(size_t)row0 * Q + e] : 0.0;
+        gather_cov(ct, 0, nc, x + (size_t)row0 * Q, Q, RG, R, RG, XC);
         __syncthreads();
         // ---- adjoint of Kxz = 2c u a^T + 2Y (own columns, registers) against d k_c / d theta of the K0 components ----------------------
         double gb[NMT][NTW][2];
@@ -298,26 +448,17 @@ k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, i
         }
         for (int cc = 0; cc < sp.n0; ++cc) {
             double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-            for (int mt = 0; mt < NMT; ++mt) {
-                if (mt < nmt) {
-                    const int t = 8 * mt + g;
-#pragma unroll
-                    for (int nt = 0; nt < NTW; ++nt) {
-                        const int j0 = colw + 8 * nt + 2 * q;
-                        double f0, f1, d20, d21;
-                        comp_pair(sp, cc, xs + t * Q, zs + j0 * Q, zs + (j0 + 1) * Q, hyp.hil2, hyp.etab, f0, f1, d20, d21);
-                        const double w0 = gb[mt][nt][0] * f0, w1 = gb[mt][nt][1] * f1;
-                        s1 += w0 + w1;
-                        s2 += w0 * d20 + w1 * d21;
-                    }
-                }
-            }
+            eval_component<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, nmt, g, q, colw,
+                                [&](int mt, int nt, double f0, double f1, double d20, double d21) {
+                                    const double w0 = gb[mt][nt][0] * f0, w1 = gb[mt][nt][1] * f1;
+                                    s1 += w0 + w1;
+                                    s2 += w0 * d20 + w1 * d21;
+                                });
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
             if (lane == 0) {
                 hypacc[wl][sp.n_ls + cc] += s1;
-                if (sp.rbf_dim[cc] >= 0) hypacc[wl][sp.ls_idx[cc]] += s2 * hyp.osc[cc] * hyp.il3[sp.ls_idx[cc]];
+                if (ct.rbf[cc]) hypacc[wl][ct.lsidx[cc]] += s2 * ct.lsw[cc];
             }
         }
         // ---- Q = Y V^T over this warp's k-slice, subject-diagonal upper tiles ; adjoint of B_p = -(c u u^T + Q) ---------------------
@@ -342,46 +483,51 @@ k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, i
             dmma(qa[4][0], qa[4][1], ya[1], vb[2]);
             dmma(qa[5][0], qa[5][1], ya[2], vb[2]);
         }
-        // gB of this lane's entries (tile tl = (i <= jt), entries (8i + g, 8jt + 2q + e)); zero outside the subject blocks
+        // sum the 8 k-slices of Q through shared memory; warp tl < 6 then owns tile tl = (i <= jt): entries (8i + g, 8jt + 2q + e)
 #pragma unroll
-        for (int tl = 0; tl < 6; ++tl) {
+        for (int tl = 0; tl < 6; ++tl)
+            *reinterpret_cast<double2*>(qred + ((wl * 6 + tl) * 32 + lane) * 2) = make_double2(qa[tl][0], qa[tl][1]);
+        __syncthreads();
+        if (wl < 6) {
+            const int tl = wl;
             const int jt = tl < 1 ? 0 : (tl < 3 ? 1 : 2);
             const int i = tl - (jt * (jt + 1)) / 2;
-            const int t = 8 * i + g;
-            const double wgt = jt > i ? -2.0 : -1.0;
+            if (jt < nmt) {
+                double qs0 = 0.0, qs1 = 0.0;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int t2 = 8 * jt + 2 * q + e;
-                const bool on = jt < nmt && t < R && t2 < R && blo[t] == blo[t2];
-                const double gB = on ? wgt * ((wl == 0 ? c * us[t] * us[t2] : 0.0) + qa[tl][e]) : 0.0;
-                qa[tl][e] = gB;
-                if (t == t2) gno += gB;
-            }
-        }
-        for (int cc = sp.n0; cc < nc; ++cc) {
-            double s1 = 0.0, s2 = 0.0;
+                for (int ww = 0; ww < 8; ++ww) {
+                    const double2 v = *reinterpret_cast<const double2*>(qred + ((ww * 6 + tl) * 32 + lane) * 2);
+                    qs0 += v.x; qs1 += v.y;
+                }
+                const int t = 8 * i + g;
+                const double wgt = jt > i ? -2.0 : -1.0;
+                double gB[2];
 #pragma unroll
-            for (int tl = 0; tl < 6; ++tl) {
-                const int jt = tl < 1 ? 0 : (tl < 3 ? 1 : 2);
-                const int i = tl - (jt * (jt + 1)) / 2;
-                if (jt < nmt) {
-                    const int t = 8 * i + g;
+                for (int e = 0; e < 2; ++e) {
+                    const int t2 = 8 * jt + 2 * q + e;
+                    const bool on = t < R && t2 < R && blo[t] == blo[t2];
+                    gB[e] = on ? wgt * (c * us[t] * us[t2] + (e ? qs1 : qs0)) : 0.0;     // adjoint of B_p, zero outside the subject blocks
+                    if (t == t2) gno += gB[e];
+                }
+                for (int cc = sp.n0; cc < nc; ++cc) {
+                    const double* XCc = XC + cc * CS * RG;
+                    double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int t2 = 8 * jt + 2 * q + e;
                         double d2;
-                        const double f = comp_one(sp, cc, xs + t * Q, xs + t2 * Q, hyp.hil2, hyp.etab, d2);
-                        const double w_ = qa[tl][e] * f;
+                        const double f = eval_rows(ct, cc, XCc, RG, t, t2, d2);
+                        const double w_ = gB[e] * f;
                         s1 += w_;
                         s2 += w_ * d2;
                     }
+                    s1 = warp_sum(s1);
+                    s2 = warp_sum(s2);
+                    if (lane == 0) {
+                        hypacc[wl][sp.n_ls + cc] += s1;
+                        if (ct.rbf[cc]) hypacc[wl][ct.lsidx[cc]] += s2 * ct.lsw[cc];
+                    }
                 }
-            }
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            if (lane == 0) {
-                hypacc[wl][sp.n_ls + cc] += s1;
-                if (sp.rbf_dim[cc] >= 0) hypacc[wl][sp.ls_idx[cc]] += s2 * hyp.osc[cc] * hyp.il3[sp.ls_idx[cc]];
             }
         }
     }
@@ -440,7 +586,7 @@ int launch_uv(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w
 template <int NTW>
 int launch_adj(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int MP = 64 * NTW;
-    const size_t smem = sizeof(double) * ((size_t)MP * p->Q + (size_t)RG * p->Q + MP + RG + RG / 2 + GT);
+    const size_t smem = sizeof(double) * ((size_t)4 * CS * MP + (size_t)NCB * CS * RG + MP + RG + 8 * 6 * 64 + RG / 2 + GT);
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_adj<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
