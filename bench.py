@@ -286,6 +286,12 @@ def main():
                                   _lib.stream_ptr(device))
         _lib.check(rc, "lvae_ng_step_f64")
 
+    if args.path == 1:
+        kernel_path = "generic"
+    elif M <= 64:
+        kernel_path = "fused (one DMMA kernel per subject pass)" if T_max <= 24 or args.path == 2 else "fused v1"
+    else:
+        kernel_path = "gemm (U/V materialised, S = U^T U and Y = V W as batched DMMA GEMMs)" if T_max <= 24 else "generic"
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)   # > 126 MB L2
     fl = algorithmic_flops(Tl, L, M, st.n_comp0, st.n_comp1, P_b)
     peak = dgemm_peak_tflops(device) if rank == 0 else None
@@ -411,7 +417,9 @@ def main():
         achieved = fl["subjects"] / (subj_ms * 1e-3) * 1e-12
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else None
-        roof = {"bound": "tensor", "kernel": "subject pass (fused kernel blocks + trisolve + S/Y contractions, FP64 DMMA)",
+        roof_kernel = ("subject pass (fused kernel blocks + trisolve + S/Y contractions, FP64 DMMA)" if M <= 64 else
+                       "subject pass (k_uv + S = U^T U GEMM + Y = V W GEMM + k_adj, FP64 DMMA)")
+        roof = {"bound": "tensor", "kernel": roof_kernel,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "cuBLAS FP64 GEMM 4096^3 measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
                                f"its HBM figure is {hbm} GB/s); DMMA issue ceiling measured 37.1 TFLOP/s (profiles/)",
@@ -429,7 +437,7 @@ def main():
                            "subjects_per_gpu": P_b, "global_batch_subjects": P_b * world, "L": L, "M": M,
                            "sharding": "subjects across ranks, all-reduce of SVGP statistics" if world > 1 else "single GPU",
                            "l2": "flushed between timed steps (256 MiB write, outside the per-step event pair)",
-                           "kernel_path": "fused" if (args.path == 2 or (args.path == 0 and M <= 64)) else "generic"},
+                           "kernel_path": kernel_path},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks.summary(),

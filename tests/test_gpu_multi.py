@@ -48,7 +48,7 @@ def _worker(rank, world, port, case, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["cfg2_small", "cfg4_ragged"])
+@pytest.mark.parametrize("case", ["cfg2_small", "cfg4_ragged", "cfg3_small"])
 def test_two_rank_sharding_matches_reference(case, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
