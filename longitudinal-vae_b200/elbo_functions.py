@@ -68,6 +68,7 @@ class _KldBound(torch.autograd.Function):
         if _CHECK == "immediate":
             call.raise_on_info()
         else:
+            call.post_info()
             _PENDING.append(call)
             if len(_PENDING) > 2:                      # the oldest one finished long ago: reading its flags does not stall
                 _PENDING.pop(0).raise_on_info()

@@ -142,8 +142,21 @@ class KldCall:
     def run(self):
         self._run(self.lib.lvae_kld_minibatch_f64, "lvae_kld_minibatch_f64")
 
+    def post_info(self):
+        """Deferred check: copy the flags to pinned host memory on the current stream without blocking."""
+        self._info_host = torch.empty(4, dtype=torch.int32).pin_memory()
+        self._info_host.copy_(self.info, non_blocking=True)
+        self._info_event = torch.cuda.Event()
+        self._info_event.record(torch.cuda.current_stream(self.device))
+
     def raise_on_info(self):
-        info = self.info.tolist()          # one device->host sync, like torch.cholesky's own check
+        ev = getattr(self, "_info_event", None)
+        if ev is not None:                 # posted earlier: wait for THAT copy only, not for the work enqueued since
+            ev.synchronize()
+            info = self._info_host.tolist()
+            self._info_event = None
+        else:
+            info = self.info.tolist()      # one device->host sync, like torch.cholesky's own check
         names = ("Kzz + eps*I", "H", "a per-subject block K1 + noise*I", "the natural-gradient update")
         for v, n in zip(info, names):
             if v:
