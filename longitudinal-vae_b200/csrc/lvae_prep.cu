@@ -1,4 +1,6 @@
-// Per-subject T x T work of the GP-prior ELBO path, one WARP per (subject, latent) task, no block barriers:
+// Per-subject T x T work of the GP-prior ELBO path, one group of NW warps per (subject, latent) task (NW = 1 for T <= 24:
+// no block barriers at all; NW = 4 for 24 < T <= 40, where three T x T scratch matrices per task leave room for only five
+// tasks per SM and one warp per task would run the SM at 4-5 warps; the warps of a group meet at a named barrier):
 //   B_p = K1(X_p, X_p) + s2 I  ->  Cholesky (in place)  ->  L^-1  ->  B_p^-1 = L^-T L^-1   (elbo_functions.py:174,179-180)
 //   K0_p (173), scalars C = 2 sum log L_tt (192), D1 = sum B^-1 o K0 (193), Bt = sum (B^-1)_tt e^{logv} (191), F (196),
 //   d_log_v, and the part of the reverse pass that only needs T x T blocks:
@@ -31,17 +33,26 @@ __device__ __forceinline__ void tri_index(int e, int& i, int& j) {
     j = e - i * (i + 1) / 2;
 }
 
-// advance (i, j) of a lower-triangle element by 32 positions (row-major, j <= i)
-__device__ __forceinline__ void tri_step32(int& i, int& j) {
-    j += 32;
+// advance (i, j) of a lower-triangle element by `n` positions (row-major, j <= i)
+__device__ __forceinline__ void tri_step(int& i, int& j, int n) {
+    j += n;
     while (j > i) { j -= i + 1; ++i; }
 }
+// barrier of the NW warps working on one task (named barrier `bar`), a plain __syncwarp for NW == 1
+template <int NW>
+__device__ __forceinline__ void gsync(int bar) {
+    if (NW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * NW) : "memory");
+}
 
-// Warp-level blocked Cholesky of the T x T matrix A (row stride ld, zero padded), 8 x 8 blocks: the diagonal block is
-// factored column by column, the panel below by one lane per row (forward substitution), the trailing matrix by DMMA.
-// dinv[k] receives 1 / L_kk.  Returns 0 or 1 + first non-positive pivot (warp-uniform).
-__device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int ld, double* __restrict__ dinv, int lane) {
-    const int g = lane >> 2, q = lane & 3;
+// Blocked Cholesky of the T x T matrix A (row stride ld, zero padded), 8 x 8 blocks, by the NW warps of a group: the
+// diagonal block is factored column by column by warp 0, the panel below by one lane per row (forward substitution), the
+// trailing matrix by DMMA (tiles dealt to the warps).  dinv[k] receives 1 / L_kk.  `bad` (1 + first non-positive pivot) is
+// only meaningful in warp 0.
+template <int NW>
+__device__ __forceinline__ int grp_cholesky(double* __restrict__ A, int T, int ld, double* __restrict__ dinv, int lane, int wg,
+                                            int bar) {
+    const int g = lane >> 2, q = lane & 3, gl = lane + 32 * wg;
     const int nb = (T + 7) >> 3;
     int bad = 0;
     // lane -> (ur, uc), 1 <= uc <= ur <= 7: its element of the 7 x 7 lower triangle updated inside a diagonal block
@@ -51,20 +62,23 @@ __device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int 
     ur += 1;
     for (int kb = 0; kb < nb; ++kb) {
         const int k0 = 8 * kb, bs = min(8, T - k0);
-        for (int k = 0; k < bs; ++k) {
-            const double akk = A[(k0 + k) * ld + k0 + k];
-            if (!(akk > 0.0) && bad == 0) bad = k0 + k + 1;
-            const double ri = rsqrt(akk);
-            __syncwarp();
-            if (lane == k) { A[(k0 + k) * ld + k0 + k] = akk * ri; dinv[k0 + k] = ri; }
-            if (lane > k && lane < bs) A[(k0 + lane) * ld + k0 + k] *= ri;
-            __syncwarp();
-            if (lane < 28 && uc > k && ur < bs)
-                A[(k0 + ur) * ld + k0 + uc] -= A[(k0 + ur) * ld + k0 + k] * A[(k0 + uc) * ld + k0 + k];
-            __syncwarp();
+        if (wg == 0) {
+            for (int k = 0; k < bs; ++k) {
+                const double akk = A[(k0 + k) * ld + k0 + k];
+                if (!(akk > 0.0) && bad == 0) bad = k0 + k + 1;
+                const double ri = rsqrt(akk);
+                __syncwarp();
+                if (lane == k) { A[(k0 + k) * ld + k0 + k] = akk * ri; dinv[k0 + k] = ri; }
+                if (lane > k && lane < bs) A[(k0 + lane) * ld + k0 + k] *= ri;
+                __syncwarp();
+                if (lane < 28 && uc > k && ur < bs)
+                    A[(k0 + ur) * ld + k0 + uc] -= A[(k0 + ur) * ld + k0 + k] * A[(k0 + uc) * ld + k0 + k];
+                __syncwarp();
+            }
         }
         if (kb + 1 < nb) {
-            for (int r = k0 + 8 + lane; r < T; r += 32) {           // panel rows: x D^T = a
+            gsync<NW>(bar);
+            for (int r = k0 + 8 + gl; r < T; r += 32 * NW) {        // panel rows: x D^T = a
                 double xr[8];
 #pragma unroll
                 for (int c_ = 0; c_ < 8; ++c_) {
@@ -77,9 +91,11 @@ __device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int 
 #pragma unroll
                 for (int c_ = 0; c_ < 8; ++c_) A[r * ld + k0 + c_] = xr[c_];
             }
-            __syncwarp();
+            gsync<NW>(bar);
+            int tl = 0;
             for (int ti = kb + 1; ti < nb; ++ti) {                   // trailing update on the lower tiles
-                for (int tj = kb + 1; tj <= ti; ++tj) {
+                for (int tj = kb + 1; tj <= ti; ++tj, ++tl) {
+                    if (NW > 1 && (tl % NW) != wg) continue;
                     const int i = 8 * ti + g, j = 8 * tj + 2 * q;
                     double c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -89,19 +105,23 @@ __device__ __forceinline__ int warp_cholesky(double* __restrict__ A, int T, int 
                     if (i < T && j + 1 < T) A[i * ld + j + 1] -= c1;
                 }
             }
-            __syncwarp();
+            gsync<NW>(bar);
         }
     }
+    gsync<NW>(bar);
     return bad;
 }
 
 // X = L^-1 (lower, T x T) into a zero-initialised X: 8 x 8 diagonal blocks by one lane per column, then the block
-// sub-diagonals X_ij = -X_ii (sum_k L_ik X_kj) on the tensor pipe.  tile: 64 doubles of per-warp scratch.
-__device__ __forceinline__ void warp_tri_inverse(const double* __restrict__ Lc, double* __restrict__ X, int T, int ld,
-                                                 const double* __restrict__ dinv, double* __restrict__ tile, int lane) {
+// sub-diagonals X_ij = -X_ii (sum_k L_ik X_kj) on the tensor pipe (blocks of a sub-diagonal dealt to the warps).
+// tile: 64 doubles of scratch per warp.
+template <int NW>
+__device__ __forceinline__ void grp_tri_inverse(const double* __restrict__ Lc, double* __restrict__ X, int T, int ld,
+                                                const double* __restrict__ dinv, double* __restrict__ tile, int lane, int wg,
+                                                int bar) {
     const int g = lane >> 2, q = lane & 3;
     const int nb = (T + 7) >> 3;
-    for (int j = lane; j < T; j += 32) {
+    for (int j = lane + 32 * wg; j < T; j += 32 * NW) {
         const int kend = min(T, (j & ~7) + 8);
         X[j * ld + j] = dinv[j];
         for (int i = j + 1; i < kend; ++i) {
@@ -110,9 +130,9 @@ __device__ __forceinline__ void warp_tri_inverse(const double* __restrict__ Lc, 
             X[i * ld + j] = -s * dinv[i];
         }
     }
-    __syncwarp();
+    gsync<NW>(bar);
     for (int d = 1; d < nb; ++d) {
-        for (int bj = 0; bj + d < nb; ++bj) {
+        for (int bj = wg; bj + d < nb; bj += NW) {
             const int bi = bj + d;
             double t0 = 0.0, t1 = 0.0;
             for (int bk = bj; bk < bi; ++bk) {
@@ -131,13 +151,14 @@ __device__ __forceinline__ void warp_tri_inverse(const double* __restrict__ Lc, 
             if (i < T) { X[i * ld + j] = x0; X[i * ld + j + 1] = x1; }
             __syncwarp();
         }
+        gsync<NW>(bar);
     }
 }
 
-template <bool TA, bool SYM>
-__device__ __forceinline__ void warp_mm(const double* __restrict__ A, const double* __restrict__ B,
-                                        double* __restrict__ C, int T, int ld, int nt8, int nk4, int g, int q) {
-    for (int ti = 0; ti < nt8; ++ti) {
+template <bool TA, bool SYM, int NW>
+__device__ __forceinline__ void grp_mm(const double* __restrict__ A, const double* __restrict__ B,
+                                       double* __restrict__ C, int T, int ld, int nt8, int nk4, int g, int q, int wg) {
+    for (int ti = SYM ? nt8 - 1 - wg : wg; SYM ? ti >= 0 : ti < nt8; ti += SYM ? -NW : NW) {   // SYM: longest rows first
         double acc[NT8MAX][2];
 #pragma unroll
         for (int tj = 0; tj < NT8MAX; ++tj) acc[tj][0] = acc[tj][1] = 0.0;
@@ -169,7 +190,8 @@ __device__ __forceinline__ void warp_mm(const double* __restrict__ A, const doub
     }
 }
 
-__global__ void __launch_bounds__(PWMAX * 32, 2)
+template <int NW>
+__global__ void __launch_bounds__(NW == 1 ? PWMAX * 32 : 512, NW == 1 ? 2 : 1)
 k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int N_b, int Tmax,
             int ld,
             const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ mu,
@@ -180,6 +202,8 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
     __shared__ double hil2[LVAE_MAXC], il3[LVAE_MAXC], osc[LVAE_MAXC], etab[LVAE_EXP_TBL];
     __shared__ double s_noise;
     const int l = blockIdx.y, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int grp = wid / NW, wg = wid % NW, gl = lane + 32 * wg, bar = 1 + grp;      // group of NW warps = one task at a time
+    constexpr int NL = 32 * NW;
     const int nc = sp.n0 + sp.n1, nh = hyp_count(sp);
     if (tid < sp.n_ls) { const double v = ls[(size_t)tid * L + l]; hil2[tid] = 0.5 / (v * v); il3[tid] = 1.0 / (v * v * v); }
     if (tid < nc) osc[tid] = os[(size_t)tid * L + l];
@@ -187,15 +211,15 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
     load_exp_table(etab);
     const int TP8 = (Tmax + 7) & ~7;
     const int asz = TP8 * ld;
-    double* A1 = sm + (size_t)wid * (3 * asz + Tmax * Q + 2 * Tmax + TP8 + 64);
+    double* A1 = sm + (size_t)grp * (3 * asz + Tmax * Q + 2 * Tmax + TP8 + 64 * NW);
     double* A2 = A1 + asz;
     double* A3 = A2 + asz;
     double* xs = A3 + asz;
     double* ev = xs + Tmax * Q;
     double* mw = ev + Tmax;
     double* dinv = mw + Tmax;          // [TP8]
-    double* tile = dinv + TP8;         // [64]
-    for (int e = lane; e < 3 * asz; e += 32) A1[e] = 0.0;
+    double* tile = dinv + TP8 + 64 * wg;   // [64] per warp
+    for (int e = gl; e < 3 * asz; e += NL) A1[e] = 0.0;
     __syncthreads();
     const int64_t* off2 = reinterpret_cast<const int64_t*>(ws + w.off2);   // (block layout only; unused when w.v2)
 
@@ -204,68 +228,67 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
 #pragma unroll
     for (int k = 0; k < NCMAX; ++k) gos[k] = gls[k] = 0.0;
 
-    const int PW = blockDim.x >> 5;
-    const int nwarps = gridDim.x * PW, gw = blockIdx.x * PW + wid;
+    const int GPC = (blockDim.x >> 5) / NW;                // groups per CTA
+    const int ngrp = gridDim.x * GPC, gg = blockIdx.x * GPC + grp;
     int Tprev = -1;
-    for (int p = gw; p < P_b; p += nwarps) {
+    for (int p = gg; p < P_b; p += ngrp) {
         const int r0 = offsets[p], T = offsets[p + 1] - r0;
         const int nt8 = (T + 7) >> 3, nk4 = (T + 3) >> 2;
-        __syncwarp();
+        gsync<NW>(bar);
         if (Tprev != -1 && T != Tprev) {          // ragged batches: restore the zero padding the DMMA tiles rely on
-            for (int e = lane; e < 3 * asz; e += 32) A1[e] = 0.0;
+            for (int e = gl; e < 3 * asz; e += NL) A1[e] = 0.0;
         }
         Tprev = T;
-        for (int e = lane; e < T * Q; e += 32) xs[e] = x[(size_t)r0 * Q + e];
-        for (int t = lane; t < T; t += 32) {
+        for (int e = gl; e < T * Q; e += NL) xs[e] = x[(size_t)r0 * Q + e];
+        for (int t = gl; t < T; t += NL) {
             const double lv = log_v[(size_t)(r0 + t) * L + l];
             ev[t] = exp(lv);
             sF += lv;
             if (w.v2) mw[t] = mu[(size_t)(r0 + t) * L + l];
         }
-        __syncwarp();
+        gsync<NW>(bar);
         // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) -------------------------------------------------
         const int ntri = T * (T + 1) / 2;
         {
             int i, j;
-            tri_index(lane, i, j);
-            for (int e = lane; e < ntri; e += 32) {
+            tri_index(gl, i, j);
+            for (int e = gl; e < ntri; e += NL) {
                 double k1 = 0.0, d2;
                 for (int cc = sp.n0; cc < nc; ++cc) k1 += osc[cc] * comp_one(sp, cc, xs + i * Q, xs + j * Q, hil2, etab, d2);
                 if (i == j) k1 += s_noise;
                 A1[i * ld + j] = k1;
                 A1[j * ld + i] = k1;
-                tri_step32(i, j);
+                tri_step(i, j, NL);
             }
         }
-        for (int e = lane; e < asz; e += 32) A2[e] = 0.0;
-        __syncwarp();
+        for (int e = gl; e < asz; e += NL) A2[e] = 0.0;
+        gsync<NW>(bar);
         // ---- blocked Cholesky in place, L^-1 into A2 (tensor pipe for the block updates) ------------------------------------
         {
-            const int bad = warp_cholesky(A1, T, ld, dinv, lane);
-            if (bad && lane == 0) atomicCAS(info + 2, 0, l * P_b + p + 1);
+            const int bad = grp_cholesky<NW>(A1, T, ld, dinv, lane, wg, bar);
+            if (bad && wg == 0 && lane == 0) atomicCAS(info + 2, 0, l * P_b + p + 1);
         }
-        for (int t = lane; t < T; t += 32) sC -= 2.0 * log(dinv[t]);                                          // 192
-        warp_tri_inverse(A1, A2, T, ld, dinv, tile, lane);
-        __syncwarp();
+        for (int t = gl; t < T; t += NL) sC -= 2.0 * log(dinv[t]);                                            // 192
+        grp_tri_inverse<NW>(A1, A2, T, ld, dinv, tile, lane, wg, bar);
         if (w.v2) {   // rows of L^-1 for the fused pass: [row][k'], k' = column inside the subject, zero padded to TP
-            double* gl = ws + w.Lrows + ((size_t)l * N_b + r0) * w.TP;
-            int i = 0, k = lane;
+            double* gl_ = ws + w.Lrows + ((size_t)l * N_b + r0) * w.TP;
+            int i = 0, k = gl;
             while (k >= w.TP) { k -= w.TP; ++i; }
-            for (int e = lane; e < T * w.TP; e += 32) {
-                gl[e] = (k <= i) ? A2[i * ld + k] : 0.0;
-                k += 32;
+            for (int e = gl; e < T * w.TP; e += NL) {
+                gl_[e] = (k <= i) ? A2[i * ld + k] : 0.0;
+                k += NL;
                 while (k >= w.TP) { k -= w.TP; ++i; }
             }
         }
         // ---- B^-1 = L^-T L^-1 into A3 --------------------------------------------------------------------------------
-        warp_mm<true, true>(A2, A2, A3, T, ld, nt8, nk4, g, q);
-        __syncwarp();
+        grp_mm<true, true, NW>(A2, A2, A3, T, ld, nt8, nk4, g, q, wg);
+        gsync<NW>(bar);
         // ---- K0_p (+ diag v) into A1 ; D1 ; adjoint of K0 = c B^-1 contracted on the fly (lower triangle, weight 2) ---
         int ti_, tj_;
-        tri_index(lane, ti_, tj_);
-        for (int e = lane; e < ntri; e += 32) {
+        tri_index(gl, ti_, tj_);
+        for (int e = gl; e < ntri; e += NL) {
             const int i = ti_, j = tj_;
-            tri_step32(ti_, tj_);
+            tri_step(ti_, tj_, NL);
             const double bi = A3[i * ld + j] * (i == j ? 1.0 : 2.0);
             double k0 = 0.0;
 #pragma unroll
@@ -282,35 +305,34 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
             A1[i * ld + j] = k0 + (i == j ? ev[i] : 0.0);
             A1[j * ld + i] = A1[i * ld + j];
         }
-        __syncwarp();
+        gsync<NW>(bar);
         // ---- X1 = (diag v + K0) B^-1 -> A2 ; X2 = B^-1 X1 -> A1 -------------------------------------------------------
-        warp_mm<false, false>(A1, A3, A2, T, ld, nt8, nk4, g, q);
-        __syncwarp();
-        warp_mm<false, false>(A3, A2, A1, T, ld, nt8, nk4, g, q);
-        __syncwarp();
+        grp_mm<false, false, NW>(A1, A3, A2, T, ld, nt8, nk4, g, q, wg);
+        gsync<NW>(bar);
+        grp_mm<false, false, NW>(A3, A2, A1, T, ld, nt8, nk4, g, q, wg);
+        gsync<NW>(bar);
         // ---- B^-1 out ; local adjoint of B_p: (B^-1 - X2) [times c at the end] ; K1 hyper-gradients ; Bt ; d_log_v -------
         if (w.v2) {
-            // rows of L^-1 (kept in A2 until X1 overwrote it: re-derive is not possible, so they were exported before X1)
             double* gb = ws + w.bmu + (size_t)l * N_b + r0;
-            for (int t = lane; t < T; t += 32) {
+            for (int t = gl; t < T; t += NL) {
                 double s = 0.0;
                 for (int k = 0; k < T; ++k) s += A3[t * ld + k] * mw[k];
                 gb[t] = s;
             }
         } else {
             double* gBi = ws + w.Bi + (size_t)l * w.Bi_stride + off2[p];
-            int i = 0, j = lane;
+            int i = 0, j = gl;
             while (j >= T) { j -= T; ++i; }
-            for (int e = lane; e < T * T; e += 32) {
+            for (int e = gl; e < T * T; e += NL) {
                 gBi[e] = A3[i * ld + j];
-                j += 32;
+                j += NL;
                 while (j >= T) { j -= T; ++i; }
             }
         }
-        tri_index(lane, ti_, tj_);
-        for (int e = lane; e < ntri; e += 32) {
+        tri_index(gl, ti_, tj_);
+        for (int e = gl; e < ntri; e += NL) {
             const int i = ti_, j = tj_;
-            tri_step32(ti_, tj_);
+            tri_step(ti_, tj_, NL);
             const double bi = A3[i * ld + j];
             const double gB = (i == j) ? bi - A1[i * ld + i] : 2.0 * bi - (A1[i * ld + j] + A1[j * ld + i]);
 #pragma unroll
@@ -331,6 +353,7 @@ k_prep_warp(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayou
         }
     }
     // ---- per-warp partial row ---------------------------------------------------------------------------------------
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wid;
     double* out = ws + w.ppart + ((size_t)gw * L + l) * (LVAE_NSCAL + nh);
     sC = warp_sum(sC); sD1 = warp_sum(sD1); sBt = warp_sum(sBt); sF = warp_sum(sF); gno = warp_sum(gno);
     if (lane == 0) {
@@ -361,28 +384,34 @@ static int ld_for(int Tmax) {
     return ld;
 }
 
-static size_t warp_doubles(int Tm, int Q) {
+static int group_warps(int Tm) { return Tm <= 24 ? 1 : 4; }
+
+static size_t group_doubles(int Tm, int Q) {
     const int ld = ld_for(Tm), TP8 = (Tm + 7) & ~7;
-    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + 2 * Tm + TP8 + 64;
+    return 3 * (size_t)TP8 * ld + (size_t)Tm * Q + 2 * Tm + TP8 + 64 * group_warps(Tm);
 }
 
-static int warps_per_cta(int Tm, int Q) {
-    int pw = (int)((200 * 1024) / (sizeof(double) * warp_doubles(Tm, Q)));
-    if (pw > PWMAX) pw = PWMAX;
-    return pw < 1 ? 1 : pw;
+// groups per CTA: as many as fit ~200 KB (NW = 4: at most 4 groups = 16 warps), at most 8 single-warp groups
+static int groups_per_cta(int Tm, int Q) {
+    const int nw = group_warps(Tm);
+    int n = (int)((200 * 1024) / (sizeof(double) * group_doubles(Tm, Q)));
+    const int cap = nw == 1 ? PWMAX : 4;
+    if (n > cap) n = cap;
+    return n < 1 ? 1 : n;
 }
 
 int lvae_prep_rows(int P_b, int L, int T_max, int Q) {
-    // partial rows per latent = warps per latent: about one wave of CTAs, a few tasks per warp
+    // partial rows per latent = warps per latent: about one wave of CTAs, a few tasks per group
     const int Tm = T_max > 0 ? T_max : 1;
-    const int pw = warps_per_cta(Tm, Q);
-    const size_t cta_bytes = sizeof(double) * pw * warp_doubles(Tm, Q) + 2048;
+    const int nw = group_warps(Tm), gpc = groups_per_cta(Tm, Q), pw = gpc * nw;
+    const size_t cta_bytes = sizeof(double) * gpc * group_doubles(Tm, Q) + 2048;
     int per_sm = (int)((227 * 1024) / cta_bytes);
     if (per_sm < 1) per_sm = 1;
+    if (nw > 1) per_sm = 1;
     if (per_sm * pw > 32) per_sm = 32 / pw > 0 ? 32 / pw : 1;
     int ctas = per_sm * 148 / L;
     if (ctas < 1) ctas = 1;
-    const int need = (P_b + pw - 1) / pw;
+    const int need = (P_b + gpc - 1) / gpc;
     if (ctas > need) ctas = need > 0 ? need : 1;
     return ctas * pw;
 }
@@ -391,20 +420,26 @@ bool lvae_prep_warp_supported(const lvae_kld_problem_t* p) {
     return p->ks.n_comp0 + p->ks.n_comp1 <= NCMAX && p->T_max <= 8 * NT8MAX;
 }
 
-int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+template <int NW>
+static int launch_prep(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int Tm = p->T_max > 0 ? p->T_max : 1;
     const int ld = ld_for(Tm);
-    const int pw = warps_per_cta(Tm, p->Q);
-    const size_t smem = sizeof(double) * (size_t)pw * warp_doubles(Tm, p->Q);
+    const int gpc = groups_per_cta(Tm, p->Q), pw = gpc * NW;
+    const size_t smem = sizeof(double) * (size_t)gpc * group_doubles(Tm, p->Q);
     static size_t attr = 0;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_prep_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_prep_warp<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         attr = smem;
     }
-    k_prep_warp<<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, Tm, ld, p->x, p->offsets,
-                                                                p->mu, p->log_v, p->lengthscale, p->outputscale, p->noise,
-                                                                0.5 * p->scale, p->d_log_v, p->workspace, p->info);
+    k_prep_warp<NW><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, Tm, ld, p->x, p->offsets,
+                                                                    p->mu, p->log_v, p->lengthscale, p->outputscale, p->noise,
+                                                                    0.5 * p->scale, p->d_log_v, p->workspace, p->info);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
+}
+
+int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
+    const int Tm = p->T_max > 0 ? p->T_max : 1;
+    return group_warps(Tm) == 1 ? launch_prep<1>(p, sp, w, st) : launch_prep<4>(p, sp, w, st);
 }
