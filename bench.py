@@ -455,12 +455,17 @@ def main():
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else None
         roof_kernel = ("subject pass (fused kernel blocks + trisolve + S/Y contractions, FP64 DMMA)" if M <= 64 else
                        "subject pass (k_uv + S = U^T U GEMM + Y = V W GEMM + k_adj, FP64 DMMA)")
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tfile) and M <= 64 and T_max <= 24:
+            ent = json.load(open(tfile)).get(f"{cfg}:spb{P_b}:k_subjects_fused2")
+            traffic = ent["traffic_bytes"] if ent else None
         roof = {"bound": "tensor", "kernel": roof_kernel,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "cuBLAS FP64 GEMM 4096^3 measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
                                f"its HBM figure is {hbm} GB/s); DMMA issue ceiling measured 37.1 TFLOP/s (profiles/)",
                 "algorithmic_flops_per_launch": fl["subjects"], "kernel_ms": subj_ms,
-                "kernel_share_of_step": subj_ms / ms_per_step, "traffic": None,
+                "kernel_share_of_step": subj_ms / ms_per_step, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/)",
                 "phase_ms": {n: float(phase_ms[:, i].mean()) for i, n in
                              enumerate(["head", "prep", "subjects", "reduce", "tail", "ng_step"])},
                 "step_algorithmic_flops": fl["step"], "step_tflops": fl["step"] / (ms_per_step * 1e-3) * 1e-12}
