@@ -91,7 +91,7 @@ class ClockSampler:
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.01)
 
     def __enter__(self):
         self.thr = threading.Thread(target=self._loop, daemon=True)
@@ -136,7 +136,7 @@ def dgemm_peak_tflops(device):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference, all host threads
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(b, n_subjects):
+def cpu_reference_step_fn(b, n_subjects, device="cpu"):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lvae_oracle as orc
     L, M = b.L, b.M
@@ -145,12 +145,12 @@ def cpu_reference_step_fn(b, n_subjects):
     k0, k1 = orc.parse_kernel_lists(L, **b.lists, id_covariate=2)
     params = []
     for c in k0 + k1:
-        c.outputscale = c.outputscale.clone().requires_grad_(True)
+        c.outputscale = c.outputscale.to(device).clone().requires_grad_(True)
         params.append(c.outputscale)
         for k in list(c.lengthscales):
-            c.lengthscales[k] = c.lengthscales[k].clone().requires_grad_(True)
+            c.lengthscales[k] = c.lengthscales[k].to(device).clone().requires_grad_(True)
             params.append(c.lengthscales[k])
-    noise = torch.ones(L, dtype=torch.float64)
+    noise = torch.ones(L, dtype=torch.float64, device=device)
     ragged = isinstance(b.T, tuple)
     state = {"m": b.m.clone(), "H": b.H.clone()}
 
@@ -169,6 +169,28 @@ def cpu_reference_step_fn(b, n_subjects):
             p_.grad = None
         return float(kld.detach().sum())
     return step
+
+
+def time_gpu_reference(b, device, steps=3, warmup=2):
+    """The same oracle port of the reference, run with stock PyTorch CUDA ops (ATen / cuBLAS / cuSOLVER) on this GPU: the
+    "existing GPU path" (SURVEY 8d).  All subjects of the minibatch, fwd + backward + NG update."""
+    import copy
+    bg = copy.copy(b)
+    for k in ("x", "mu", "log_v", "z", "m", "H"):
+        setattr(bg, k, getattr(b, k).to(device))
+    with torch.device(device):
+        step = cpu_reference_step_fn(bg, b.P, device=device)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / steps
+    return b.P / (ms * 1e-3), ms
 
 
 def time_cpu(b, n_subjects, steps, warmup):
@@ -310,16 +332,17 @@ def main():
     launches0 = ops.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     phase_ms = np.zeros((args.steps, 6))
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(1.0)                       # L2 flush between timed steps (outside the event pair)
-            ev[i][0].record()
-            device_step()
-            ev[i][1].record()
-            for ph in range(6):                    # per-kernel CUDA-event durations (syncs on this step's events)
-                phase_ms[i, ph] = lib.lvae_profile_last_ms(ph)
-        barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()                             # sampled through the device-timed AND the end-to-end timed regions
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(1.0)                           # L2 flush between timed steps (outside the event pair)
+        ev[i][0].record()
+        device_step()
+        ev[i][1].record()
+        for ph in range(6):                        # per-kernel CUDA-event durations (syncs on this step's events)
+            phase_ms[i, ph] = lib.lvae_profile_last_ms(ph)
+    barrier()
     launches = ops.launch_count() - launches0
     lib.lvae_profile_enable(0)
     total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
@@ -405,6 +428,7 @@ def main():
     main.wait_event(out_done)                              # the last step's results have reached host memory
     e1.record()
     barrier()
+    clocks.__exit__(None, None, None)
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -449,6 +473,15 @@ def main():
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"oracle port of the reference (torch CPU FP64, {cores} threads): {n_sub} of the {args.spb} "
                              f"subjects per step, fwd + backward + NG update, 3 steps after 1 warm-up ({dt:.2f} s/step)"}
+        gpu_ref = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, ms = time_gpu_reference(make_problem(cfg, args.spb, 0, 1, args.L, args.M), device)
+                gpu_ref = {"value": v, "unit": UNIT, "ms_per_step": ms,
+                           "what": "oracle port of the reference with stock PyTorch CUDA ops (ATen/cuBLAS/cuSOLVER) on this "
+                                   "GPU, device-resident inputs, all subjects of the minibatch, fwd + backward + NG update"}
+            except Exception as ex:   # the baseline is informative only
+                gpu_ref = {"unavailable": repr(ex)[:200]}
         subj_ms = float(phase_ms[:, 2].mean())
         achieved = fl["subjects"] / (subj_ms * 1e-3) * 1e-12
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -484,7 +517,8 @@ def main():
                         "how": "public API (minibatch_KLD_upper_bound + backward + natural_gradient_step); every step copies "
                                "x, mu, log_v from pinned host memory and returns kld, d_mu, d_log_v to pinned host memory; the "
                                "copies of neighbouring steps overlap the compute on two copy streams"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks.summary(),
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
+                "clocks": clocks.summary(),
                 "finite": finite}
         if lat:
             line["latency_point"] = lat

@@ -230,6 +230,27 @@ def test_big_path_matches_generic_kernels(cfg, P, L, M, ng):
             assert rel(a[k], r[k]) < TOL, k
 
 
+@pytest.mark.parametrize("P,L,M,T", [(40, 3, 128, (5, 24)), (1, 2, 65, 24), (23, 2, 129, (1, 7)), (60, 2, 256, (20, 24))])
+def test_big_path_edge_shapes_vs_generic(P, L, M, T):
+    """GEMM-based path on ragged groups (several subjects per 24-row group, T = 1 subjects, a single subject, M = 65 / 129
+    just over a 64-wide block) with the 6-component cfg4 kernel, against the generic kernels."""
+    from lvae_b200 import synth
+    b = synth.make_batch("cfg4", P=P, L=L, M=1, T=T, seed=99)                 # the data rows
+    bz = synth.make_batch("cfg4", P=60, L=L, M=M, T=(5, 24), seed=98)         # inducing points, m, H from a larger set
+    b.z, b.m, b.H = bz.z, bz.m, bz.H
+    n_ls, n_c = 4, 6
+    ls, os_, noise = synth.perturbed_hypers(n_ls, n_c, L, seed=3, noise_trainable=True)
+    g = dict(lists=b.lists, lengthscale=ls.numpy(), outputscale=os_.numpy(), noise=noise.numpy(), mu=b.mu.numpy(),
+             log_v=b.log_v.numpy(), m=b.m.numpy(), H=b.H.numpy(), x=b.x.numpy(), z=b.z.numpy(), offsets=b.offsets,
+             natural_gradient=True, ragged=True, P_tot=3 * P, N_tot=3 * b.x.shape[0], eps=1e-6)
+    a = run_cuda_case(g, path=0)
+    r = run_cuda_case(g, path=1)
+    assert abs(a["kld"] - r["kld"]) <= 1e-7 * abs(r["kld"])
+    for k in r:
+        if k != "kld":
+            assert rel(a[k], r[k]) < TOL, k
+
+
 def test_natural_gradient_step_big_m():
     """training.py:129-135 for M > 64 (blocked Cholesky / inverse on DMMA GEMMs) vs the oracle, with and without the
     head's H^-1."""
