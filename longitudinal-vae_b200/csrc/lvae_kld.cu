@@ -6,6 +6,8 @@
 //   tail     per latent : D, E, KL[q(u)||p(u)], kld, grad_m, grad_H (or d_m, d_H), Kzz adjoint -> hyper-gradients
 // Formulas and line references: SURVEY.md 8(a); elbo_functions.py:144-216, 219-307.
 // The M <= 64 fast path replaces `subjects` by the DMMA kernel of lvae_subjects_fused.cu.
+#include <stdlib.h>
+
 #include "lvae_host.h"
 #include "lvae_kld.h"
 #include "lvae_linalg.cuh"
@@ -596,6 +598,46 @@ __global__ void __launch_bounds__(256) k_ng_step(double* __restrict__ m, double*
 // ---------------------------------------------------------------------------------------------------------------
 // host entry points
 // ---------------------------------------------------------------------------------------------------------------
+// The head (per-latent M x M work) does not depend on the minibatch rows and the prep kernel does not depend on the
+// head, so lvae_kld_head_f64 forks onto a per-device side stream (event fork / join, capture-safe) and the subject kernel
+// joins it: head and prep overlap.  LVAE_NO_OVERLAP=1 keeps everything on the caller's stream.
+namespace {
+constexpr int MAXDEV = 16;
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool pending = false;
+};
+SideStream g_side[MAXDEV];
+int g_overlap = -1;
+
+SideStream* side_for_current_device() {
+    if (g_overlap < 0) {
+        const char* e = getenv("LVAE_NO_OVERLAP");
+        g_overlap = (e && e[0] == '1') ? 0 : 1;
+    }
+    if (!g_overlap) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+    SideStream* s = &g_side[dev];
+    if (!s->st) {
+        if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) { s->st = nullptr; return nullptr; }
+        cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming);
+    }
+    return s;
+}
+// make `user` wait for a head that was forked onto the side stream
+void join_head(cudaStream_t user) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return;
+    SideStream* s = &g_side[dev];
+    if (s->pending) {
+        cudaStreamWaitEvent(user, s->join, 0);
+        s->pending = false;
+    }
+}
+}  // namespace
 static size_t prep_smem(const DevSpec& sp, int Tmax, int Q) {
     return sizeof(double) * ((size_t)(5 + sp.n0 + sp.n1) * Tmax * Tmax + (size_t)Tmax * Q + Tmax);
 }
@@ -609,22 +651,33 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     if (rc) return rc;
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
-    lvae_prof_begin(0, (cudaStream_t)stream);
+    cudaStream_t user = (cudaStream_t)stream, hs = user;
+    join_head(user);                               // a previous head nobody joined yet (defensive)
+    // overlap only pays when the prep kernel leaves SMs idle (small minibatches, the reference's default of 20 subjects per
+    // batch); at throughput batch sizes the head's 512-thread CTAs just take SMs away from prep
+    SideStream* side = ((int64_t)p->P_b * p->L < 148 * 32) ? side_for_current_device() : nullptr;
+    if (side) {
+        cudaEventRecord(side->fork, user);         // everything enqueued so far (previous step's tail / NG update) comes first
+        cudaStreamWaitEvent(side->st, side->fork, 0);
+        hs = side->st;
+    }
+    lvae_prof_begin(0, hs);
     if (w.big) {
-        rc = lvae_head_big_launch(p, sp, w, (cudaStream_t)stream);
-        lvae_prof_end(0, (cudaStream_t)stream);
-        return rc;
+        rc = lvae_head_big_launch(p, sp, w, hs);
+    } else if (p->M <= 64 && p->path != 1) {
+        rc = lvae_head64_launch(p, sp, w, hs);
+    } else {
+        k_head<<<p->L, 256, 0, hs>>>(sp, w, p->L, p->M, p->Q, p->z, p->m, p->H, p->lengthscale, p->outputscale, p->eps,
+                                     0.5 * p->scale, p->workspace, p->info);
+        LVAE_COUNT_LAUNCH();
+        rc = lvae_cuda_rc(cudaGetLastError());
     }
-    if (p->M <= 64 && p->path != 1) {
-        rc = lvae_head64_launch(p, sp, w, (cudaStream_t)stream);
-        lvae_prof_end(0, (cudaStream_t)stream);
-        return rc;
+    lvae_prof_end(0, hs);
+    if (side) {
+        cudaEventRecord(side->join, side->st);
+        side->pending = true;
     }
-    k_head<<<p->L, 256, 0, (cudaStream_t)stream>>>(sp, w, p->L, p->M, p->Q, p->z, p->m, p->H, p->lengthscale,
-                                                   p->outputscale, p->eps, 0.5 * p->scale, p->workspace, p->info);
-    lvae_prof_end(0, (cudaStream_t)stream);
-    LVAE_COUNT_LAUNCH();
-    return lvae_cuda_rc(cudaGetLastError());
+    return rc;
 }
 
 extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) {
@@ -658,6 +711,7 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             LVAE_COUNT_LAUNCH();
         }
         lvae_prof_end(1, st);
+        join_head(st);                             // W, a (head) are needed from here on
         if (w.big) {
             lvae_prof_begin(2, st);
             rc = lvae_subjects_big_launch(p, sp, w, st);
@@ -690,6 +744,7 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             LVAE_COUNT_LAUNCH();
         }
     } else {
+        join_head(st);
         cudaError_t e = cudaMemsetAsync(p->workspace + w.part, 0, sizeof(double) * ((size_t)w.nchunk * p->L * w.stride), st);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         e = cudaMemsetAsync(p->workspace + w.ppart, 0, sizeof(double) * ((size_t)w.nprep * p->L * (LVAE_NSCAL + w.nh)), st);
@@ -715,6 +770,7 @@ extern "C" int lvae_kld_tail_f64(const lvae_kld_problem_t* p, void* stream) {
     if (rc) return rc;
     KldLayout w = lvae_layout(p);
     w.Bi_stride = p->sum_T2;
+    join_head((cudaStream_t)stream);
     lvae_prof_begin(4, (cudaStream_t)stream);
     if (w.big) {
         rc = lvae_tail_big_launch(p, sp, w, (cudaStream_t)stream);
