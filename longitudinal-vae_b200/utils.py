@@ -87,3 +87,107 @@ class VaryingLengthBatchSampler(BatchSampler):
                 members.add(subject)
             rows.append(row)
         yield rows
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GP posterior-mean prediction (utils.py:115-345), SURVEY 8f-2.  Same call signatures as the reference; forward only.
+# Kernel matrices come from lvae_kernel_dense_f64 / lvae_kernel_blocks_f64, the per-subject and M x M factorisations and
+# explicit inverses from lvae_potrf_batched_f64 / lvae_potri_batched_f64, S = K0zx B^-1 K0xz from the batched DMMA GEMM;
+# the remaining matrix-vector products are torch.matmul on the device.  No CPU fallback.
+# ---------------------------------------------------------------------------------------------------------------
+def _spd_inverse(A):
+    from . import ops
+    return ops.potri_batched(ops.potrf_batched(A))
+
+
+def _predict_one(L, covar_module0, covar_module1, likelihoods, x, test_x, mu, z, id_covariate, eps):
+    """x [N,Q] prediction (training) rows, mu [N,L], z [L,M,Q] | [M,Q]; returns Z_pred [N*, L]."""
+    from . import ops
+    from .elbo_functions import _noise_of, _structure_of, group_by_subject
+    if not x.is_cuda:
+        raise RuntimeError("lvae_b200: prediction needs CUDA tensors (no CPU fallback)")
+    f64 = torch.float64
+    x, test_x, mu = x.to(f64), test_x.to(f64), mu.to(f64).reshape(x.shape[0], L)
+    z = z.to(f64)
+    if z.dim() == 2:
+        z = z.unsqueeze(0).expand(L, -1, -1)
+    z = z.contiguous()
+    order, offsets, T_max, sum_T2 = group_by_subject(x[:, id_covariate])      # utils.py:160-163 (sorted unique ids)
+    if order is not None:
+        x, mu = x[order], mu[order]
+    N, M = x.shape[0], z.shape[1]
+    st, ls, os_ = _structure_of(covar_module0, covar_module1, L, x.device)
+    ls, os_ = ls.detach(), os_.detach()
+    noise = _noise_of(likelihoods, L, f64, x.device).detach().contiguous()
+    K0xz = ops.kernel_dense(st, ls, os_, x, z, "k0")                              # [L,N,M]
+    K0zz = ops.kernel_dense(st, ls, os_, z, z, "k0") + eps * torch.eye(M, dtype=f64, device=x.device)
+    K0Xz = ops.kernel_dense(st, ls, os_, test_x, z, "k0")                         # [L,N*,M]
+    # per-subject B_p = K1 + noise I, explicit inverses (utils.py:165-176), grouped by the number of rows per subject
+    blocks = ops.kernel_blocks(st, ls, os_, x, offsets, sum_T2, "k1", diag_add=noise)      # flat [L, sum T^2]
+    off = offsets.to(torch.int64).cpu()
+    Ts = (off[1:] - off[:-1])
+    off2 = torch.zeros_like(off)
+    off2[1:] = torch.cumsum(Ts * Ts, 0)
+    muL = mu.t().contiguous()                                                     # [L,N]
+    iB_K0xz = torch.empty_like(K0xz)
+    iB_mu = torch.empty(L, N, dtype=f64, device=x.device)
+    groups = []
+    for T in torch.unique(Ts).tolist():
+        subj = torch.nonzero(Ts == T).reshape(-1)
+        n = subj.numel()
+        bidx = (off2[subj].unsqueeze(1) + torch.arange(T * T)).reshape(-1).to(x.device)       # block entries
+        ridx = (off[subj].unsqueeze(1) + torch.arange(T)).reshape(-1).to(x.device)            # rows
+        B = blocks[:, bidx].reshape(L * n, T, T)
+        iB = _spd_inverse(B)                                                       # [L*n,T,T]
+        Kx = K0xz[:, ridx].reshape(L * n, T, M)
+        iB_K0xz[:, ridx] = torch.bmm(iB, Kx).reshape(L, n * T, M)
+        iB_mu[:, ridx] = torch.bmm(iB, muL[:, ridx].reshape(L * n, T, 1)).reshape(L, n * T)
+        groups.append((ridx, iB, n, T))
+    H = K0zz + ops.gemm_batched(K0xz, iB_K0xz, trans_a=True)                       # K0zz + K0zx B^-1 K0xz
+    H = 0.5 * (H + H.transpose(1, 2))
+    rhs = torch.bmm(K0xz.transpose(1, 2), iB_mu.unsqueeze(2))                      # [L,M,1]
+    t1 = torch.bmm(K0xz, torch.bmm(_spd_inverse(H), rhs)).squeeze(2)               # K0xz H^-1 K0zx B^-1 mu   [L,N]
+    mu_tilde = iB_mu.clone()
+    for ridx, iB, n, T in groups:
+        mu_tilde[:, ridx] -= torch.bmm(iB, t1[:, ridx].reshape(L * n, T, 1)).reshape(L, n * T)
+    pred0 = torch.bmm(K0Xz, torch.bmm(_spd_inverse(K0zz), torch.bmm(K0xz.transpose(1, 2), mu_tilde.unsqueeze(2))))
+    # id-dependent part: K1(X*, X[mask]) mu_tilde[mask] over the subjects that occur in the test set (utils.py:187-206)
+    test_subjects = torch.unique(test_x[:, id_covariate])
+    mask = torch.isin(x[:, id_covariate], test_subjects)
+    pred1 = torch.zeros_like(pred0)
+    if bool(mask.any()):
+        K1Xx = ops.kernel_dense(st, ls, os_, test_x, x[mask].contiguous(), "k1")   # [L,N*,Nmask]
+        pred1 = torch.bmm(K1Xx, mu_tilde[:, mask].unsqueeze(2))
+    return (pred0 + pred1).squeeze(2).t().contiguous()
+
+
+def _predict_any(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list, id_covariate, eps):
+    if isinstance(covar_module0, (list, tuple)):                                   # one un-batched module per latent dimension
+        cols = [_predict_one(1, covar_module0[i], covar_module1[i], likelihoods[i], prediction_x, test_x, mu[:, i:i + 1],
+                             zt_list[i], id_covariate, eps) for i in range(latent_dim)]
+        return torch.cat(cols, dim=1)
+    return _predict_one(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list,
+                        id_covariate, eps)
+
+
+def batch_predict_varying_T(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list,
+                            id_covariate, eps):
+    """GP posterior-mean prediction for subjects with varying numbers of rows (utils.py:115-208).  Z_pred [N*, L]."""
+    return _predict_any(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list,
+                        id_covariate, eps)
+
+
+def batch_predict(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list, P, T,
+                  id_covariate, eps):
+    """GP posterior-mean prediction, exactly T rows per subject in subject-major order (utils.py:210-299).  The reference
+    reshapes by position ([P, T, Q], no id check); so does this: row blocks of T consecutive rows are the subjects."""
+    if prediction_x.shape[0] != P * T:
+        raise RuntimeError(f"shape '[{P}, {T}, {prediction_x.shape[1]}]' is invalid for input of size {prediction_x.numel()}")
+    return _predict_any(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list,
+                        id_covariate, eps)
+
+
+def predict(covar_module0, covar_module1, likelihood, train_xt, test_x, mu, z, P, T, id_covariate, eps):
+    """Single-latent prediction helper (utils.py:301-345): un-batched kernels, mu [N], z [M,Q]; returns Z_pred [N*]."""
+    return _predict_one(1, covar_module0, covar_module1, likelihood, train_xt, test_x, mu.reshape(-1, 1), z, id_covariate,
+                        eps).reshape(-1)

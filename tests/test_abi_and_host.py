@@ -76,6 +76,14 @@ def test_product_ops_fail_loudly_without_cuda():
     with pytest.raises(RuntimeError):
         EF.minibatch_KLD_upper_bound(cm0, cm1, GaussianLikelihood(batch_shape=torch.Size([2])), 2, b.m, b.H, b.x, b.mu,
                                      b.log_v, b.z, 2, 2, 20, True, 1e-6)
+    # the evaluation-side functions (prediction, DUBO) route through the same ops: no CPU fallback either
+    from lvae_b200 import utils as U
+    from lvae_b200.validation import validation_dubo
+    lik = GaussianLikelihood(batch_shape=torch.Size([2]))
+    with pytest.raises(RuntimeError):
+        U.batch_predict_varying_T(2, cm0, cm1, lik, b.x, b.x[:5], b.mu, b.z, 2, 1e-6)
+    with pytest.raises(RuntimeError):
+        validation_dubo(2, cm0, cm1, lik, b.x, b.mu, b.log_v, b.z, 2, 20, 1e-6)
 
 
 def test_samplers_match_reference_golden():
