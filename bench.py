@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic kernels, 2 fused DMMA kernel")
     ap.add_argument("--cpu-subjects", type=int, default=100, help="subjects in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
+                    help="N > 1: statistics exchange by NCCL all-reduce or by the peer-memory kernel (symmetric memory)")
     ap.add_argument("--latency-point", action="store_true", help="also time spb=20 (the reference's default batch)")
     return ap.parse_args()
 
@@ -91,7 +93,7 @@ class ClockSampler:
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.01)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.thr = threading.Thread(target=self._loop, daemon=True)
@@ -296,12 +298,24 @@ def main():
     ng_info = torch.zeros(4, dtype=torch.int32, device=device)
     lr = 1e-3
 
+    exchange_note = None
+    if dist is not None and args.exchange == "p2p":       # all ranks agree on the exchange path before any timed work
+        ok = 1
+        try:
+            from lvae_b200 import distributed as D
+            D.peer_stats(dist.group.WORLD, call.stats.numel(), device)
+        except Exception as ex:
+            ok, exchange_note = 0, f"symmetric memory unavailable ({repr(ex)[:120]}): NCCL all-reduce"
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            args.exchange = "nccl"
+            exchange_note = exchange_note or "a peer could not map symmetric memory: NCCL all-reduce"
+
     def device_step():
         call.bind(x, offsets, mu, lv, z, m.view(L, M), H, ls, os_, noise, P_tot / (P_b * world), const, 1e-6)
         call.head()
-        call.subjects()
-        if dist is not None:
-            dist.all_reduce(call.stats)
+        EF.exchange_stats(call, dist.group.WORLD if dist is not None else None, args.exchange)
         call.tail()
         rc = lib.lvae_ng_step_f64(_lib.ptr(m), _lib.ptr(H), _lib.ptr(call.grad_m), _lib.ptr(call.grad_H),
                                   _lib.ptr(call.Hinv), lr, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
@@ -333,7 +347,8 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     phase_ms = np.zeros((args.steps, 6))
     clocks = ClockSampler(local_rank)
-    clocks.__enter__()                             # sampled through the device-timed AND the end-to-end timed regions
+    if rank == 0:                                  # rank 0's GPU, sampled through the device-timed AND the end-to-end timed regions
+        clocks.__enter__()
     barrier()
     for i in range(args.steps):
         flush.fill_(1.0)                           # L2 flush between timed steps (outside the event pair)
@@ -362,7 +377,7 @@ def main():
     out_lv = torch.empty_like(b.log_v).pin_memory()
     out_kld = torch.empty(1, dtype=torch.float64).pin_memory()
     if dist is not None:
-        EF.set_process_group(dist.group.WORLD)
+        EF.set_process_group(dist.group.WORLD, args.exchange)
     EF.set_error_check("deferred")          # no device sync inside the op; failures still raise (check_errors below)
     state = {"m": m, "H": H}
 
@@ -428,7 +443,8 @@ def main():
     main.wait_event(out_done)                              # the last step's results have reached host memory
     e1.record()
     barrier()
-    clocks.__exit__(None, None, None)
+    if rank == 0:
+        clocks.__exit__(None, None, None)
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -509,7 +525,9 @@ def main():
                                        f"{st.n_comp0}+{st.n_comp1} additive components, one minibatch of {P_b * world} subjects "
                                        f"per step (bound + all gradients + NG update)",
                            "subjects_per_gpu": P_b, "global_batch_subjects": P_b * world, "L": L, "M": M,
-                           "sharding": "subjects across ranks, all-reduce of SVGP statistics" if world > 1 else "single GPU",
+                           "sharding": (f"subjects across ranks, SVGP statistics summed by {'the peer-memory kernel over NVLink (symmetric memory)' if args.exchange == 'p2p' else 'NCCL all-reduce'}"
+                                        if world > 1 else "single GPU"),
+                           "exchange_note": exchange_note,
                            "l2": "flushed between timed steps (256 MiB write, outside the per-step event pair)",
                            "kernel_path": kernel_path},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -152,6 +152,12 @@ int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* g
 int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p);
 int64_t lvae_ng_workspace_doubles(int32_t L, int32_t M);
 
+/* One-shot all-reduce of the statistics row over NVLink peer memory (the exchange step of the subject-sharded path):
+ * out[i] = sum_r peer_r[i], summed in rank order so every GPU obtains bit-identical results.  peer_ptrs: HOST array of
+ * `world` device pointers (16-byte aligned) to the peers' buffers mapped into this process (e.g. torch symmetric memory);
+ * the caller issues the inter-GPU barrier that makes those buffers complete before this call (distributed.py). */
+int lvae_peer_sum_f64(const uint64_t* peer_ptrs, int32_t world, int64_t n, double* out, void* stream);
+
 /* Optional per-phase device timing with CUDA events on the launch stream (bench.py's roofline leg).
  * phase: 0 head, 1 prep, 2 subjects, 3 reduce, 4 tail, 5 ng_step.  lvae_profile_last_ms synchronises on the event. */
 int lvae_profile_enable(int on);

@@ -18,7 +18,7 @@ CAT, BIN = 0, 1
 EXPORTS = ["lvae_kernel_dense_f64", "lvae_kernel_blocks_f64", "lvae_potrf_batched_f64", "lvae_potri_batched_f64",
            "lvae_kld_stats_stride", "lvae_kld_workspace_doubles", "lvae_kld_head_f64", "lvae_kld_subjects_f64",
            "lvae_kld_tail_f64", "lvae_kld_minibatch_f64", "lvae_ng_step_f64", "lvae_launch_count", "lvae_version",
-           "lvae_profile_enable", "lvae_profile_last_ms", "lvae_debug_exp_neg_f64", "lvae_kld_hinv_offset", "lvae_gemm_batched_f64", "lvae_ng_workspace_doubles"]
+           "lvae_profile_enable", "lvae_profile_last_ms", "lvae_debug_exp_neg_f64", "lvae_kld_hinv_offset", "lvae_gemm_batched_f64", "lvae_ng_workspace_doubles", "lvae_peer_sum_f64"]
 
 _dp = C.c_void_p
 
@@ -70,6 +70,8 @@ def load():
         getattr(lib, name).argtypes = [pp, vp]
         getattr(lib, name).restype = C.c_int
     lib.lvae_ng_step_f64.argtypes = [vp, vp, vp, vp, vp, dbl, i32, i32, vp, vp, vp]
+    lib.lvae_peer_sum_f64.argtypes = [C.POINTER(C.c_uint64), i32, i64, vp, vp]
+    lib.lvae_peer_sum_f64.restype = C.c_int
     lib.lvae_ng_workspace_doubles.argtypes = [i32, i32]
     lib.lvae_ng_workspace_doubles.restype = i64
     lib.lvae_kld_hinv_offset.argtypes = [pp]

@@ -247,5 +247,44 @@ extern "C" int lvae_debug_exp_neg_f64(const double* x, double* out, int32_t n, v
     return lvae_cuda_rc(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// one-shot all-reduce of the SVGP statistics over NVLink peer memory: every rank sums the peers' buffers (mapped into
+// this process, e.g. torch symmetric memory) in RANK ORDER, so all ranks obtain bit-identical sums.  The caller provides
+// the inter-GPU barrier before (peers' buffers complete) — see distributed.py.
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerPtrs { const double* p[16]; };
+__global__ void __launch_bounds__(256) k_peer_sum(PeerPtrs pp, int world, int64_t n, double* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; 2 * i < n; i += stride) {
+        if (2 * i + 1 < n) {
+            double2 acc = make_double2(0.0, 0.0);
+            for (int r = 0; r < world; ++r) {
+                const double2 v = *reinterpret_cast<const double2*>(pp.p[r] + 2 * i);
+                acc.x += v.x; acc.y += v.y;
+            }
+            *reinterpret_cast<double2*>(out + 2 * i) = acc;
+        } else {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += pp.p[r][2 * i];
+            out[2 * i] = acc;
+        }
+    }
+}
+extern "C" int lvae_peer_sum_f64(const uint64_t* peer_ptrs, int32_t world, int64_t n, double* out, void* stream) {
+    if (!peer_ptrs || world <= 0 || world > 16 || n < 0 || !out) return LVAE_E_BADARG;
+    if (n == 0) return 0;
+    PeerPtrs pp;
+    for (int r = 0; r < 16; ++r) pp.p[r] = r < world ? reinterpret_cast<const double*>(peer_ptrs[r]) : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (peer_ptrs[r] & 15) return LVAE_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(out) & 15) return LVAE_E_BADARG;
+    int blocks = (int)((n / 2 + 255) / 256);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    k_peer_sum<<<blocks, 256, 0, (cudaStream_t)stream>>>(pp, world, n, out);
+    LVAE_COUNT_LAUNCH();
+    return lvae_cuda_rc(cudaGetLastError());
+}
+
 extern "C" int64_t lvae_launch_count(void) { return lvae_launch_counter(); }
 extern "C" const char* lvae_version(void) { return "lvae_b200 0.1 (sm_100a, fp64)"; }

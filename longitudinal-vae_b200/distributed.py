@@ -35,16 +35,64 @@ def shard_rows(offsets, rank, world_size):
     return int(offsets[p_lo]), int(offsets[p_hi]), offsets[p_lo:p_hi + 1] - offsets[p_lo]
 
 
-def enable(group=None):
-    """Route the statistics all-reduce of minibatch_KLD_upper_bound[_iter] through `group` (default: WORLD).
-    After this, every rank passes ITS rows; P_batch / P_in_current_batch remain the GLOBAL minibatch subject counts."""
+class PeerStats:
+    """The exchange step over NVLink peer memory instead of an NCCL all-reduce: every rank's reduce kernel writes its
+    statistics row into a symmetric-memory buffer (torch.distributed._symmetric_memory, mapped into all ranks of the node),
+    one device-side barrier makes the rows visible, and `lvae_peer_sum_f64` sums the peers' rows in rank order — one
+    P2P read of (world x 0.9 MB at cfg2) per GPU, bit-identical results on all ranks.  Two buffers alternate between
+    steps, so a rank that runs ahead never overwrites a row a slower peer is still reading."""
+
+    def __init__(self, group, numel, device):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.numel = int(numel) + (int(numel) & 1)                  # keep both halves 16-byte aligned
+        self.buf = symm_mem.empty(2 * self.numel, dtype=torch.float64, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.world = self.hdl.world_size
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.step = 0
+        self._arr = [(C.c_uint64 * self.world)(*[p + h * self.numel * 8 for p in self.ptrs]) for h in range(2)]
+
+    def region(self):
+        """This step's local destination (the reduce kernel writes here)."""
+        h = self.step & 1
+        return self.buf[h * self.numel:(h + 1) * self.numel]
+
+    def all_reduce_into(self, out):
+        from . import _lib
+        h = self.step & 1
+        self.hdl.barrier(channel=h)                                 # all ranks' rows of this step are complete and visible
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.load().lvae_peer_sum_f64(self._arr[h], self.world, out.numel(), _lib.ptr(out),
+                                                     _lib.stream_ptr(out.device)), "lvae_peer_sum_f64")
+        self.step += 1
+        return out
+
+
+_PEER = {}
+
+
+def peer_stats(group, numel, device):
+    key = (id(group), int(numel), str(device))
+    if key not in _PEER:
+        _PEER[key] = PeerStats(group, numel, device)
+    return _PEER[key]
+
+
+def enable(group=None, exchange="nccl"):
+    """Route the statistics exchange of minibatch_KLD_upper_bound[_iter] through `group` (default: WORLD).
+    After this, every rank passes ITS rows; P_batch / P_in_current_batch remain the GLOBAL minibatch subject counts.
+    exchange: "nccl" (one all_reduce) | "p2p" (symmetric memory + lvae_peer_sum_f64, single node, see PeerStats)."""
     if not dist.is_initialized():
         raise RuntimeError("lvae_b200.distributed.enable: torch.distributed is not initialised")
-    elbo_functions.set_process_group(group if group is not None else dist.group.WORLD)
+    if exchange not in ("nccl", "p2p"):
+        raise ValueError(exchange)
+    elbo_functions.set_process_group(group if group is not None else dist.group.WORLD, exchange)
 
 
 def disable():
     elbo_functions.set_process_group(None)
+    _PEER.clear()
 
 
 def all_reduce_stats(stats, group=None):

@@ -19,10 +19,29 @@ _CHECK = "immediate"  # Cholesky-failure check: "immediate" (one device sync per
 _PENDING = []        # KldCall objects whose info flags have not been read yet (deferred mode)
 
 
-def set_process_group(group):
+_EXCHANGE = "nccl"   # how the statistics row is summed over ranks: "nccl" all-reduce | "p2p" (distributed.PeerStats)
+
+
+def set_process_group(group, exchange="nccl"):
     """Shard mode: every rank passes ITS rows; P_batch / P_in_current_batch stay GLOBAL minibatch subject counts."""
-    global _GROUP
-    _GROUP = group
+    global _GROUP, _EXCHANGE
+    _GROUP, _EXCHANGE = group, exchange
+
+
+def exchange_stats(call, group, exchange):
+    """The one exchange step of the sharded path, between the subject pass and the tail (call.subjects() included)."""
+    if group is None:
+        call.subjects()
+    elif exchange == "p2p":
+        from . import distributed
+        ps = distributed.peer_stats(group, call.stats.numel(), call.device)
+        call.set_stats(ps.region())                 # the reduce kernel writes straight into symmetric memory
+        call.subjects()
+        call.set_stats(call.stats)
+        ps.all_reduce_into(call.stats)
+    else:
+        call.subjects()
+        torch.distributed.all_reduce(call.stats, group=group)      # SVGP sufficient statistics over NVLink
 
 
 def set_kernel_path(path):
@@ -61,9 +80,7 @@ class _KldBound(torch.autograd.Function):
         call.bind(x, offsets, mu, log_v, z, m.reshape(L, M), H, lengthscale, outputscale, noise, meta["scale"],
                   meta["const_term"], meta["eps"])
         call.head()
-        call.subjects()
-        if _GROUP is not None:
-            torch.distributed.all_reduce(call.stats, group=_GROUP)      # SVGP sufficient statistics over NVLink
+        exchange_stats(call, _GROUP, _EXCHANGE)
         call.tail()
         if _CHECK == "immediate":
             call.raise_on_info()

@@ -126,6 +126,10 @@ class KldCall:
         self._held = (held, offsets_dev)
         return self
 
+    def set_stats(self, t):
+        """Point the statistics row at `t` (e.g. a symmetric-memory region) for the next call."""
+        self.p.stats = t.data_ptr()
+
     def _run(self, fn, what):
         with torch.cuda.device(self.device):
             check(fn(C.byref(self.p), stream_ptr(self.device)), what)

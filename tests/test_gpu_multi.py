@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, case, out_dir):
+def _worker(rank, world, port, case, out_dir, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -34,7 +34,7 @@ def _worker(rank, world, port, case, out_dir):
     mu = t("mu")[lo:hi].clone().requires_grad_(True)
     lv = t("log_v")[lo:hi].clone().requires_grad_(True)
     P_b = len(g["offsets"]) - 1
-    D.enable()
+    D.enable(exchange=exchange)
     if bool(g["ragged"]):
         kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, t("m"), t("H"), t("x")[lo:hi], mu, lv, t("z"),
                                                         int(g["P_tot"]), P_b, int(g["N_tot"]), True, 2, float(g["eps"]))
@@ -48,13 +48,15 @@ def _worker(rank, world, port, case, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 @pytest.mark.parametrize("case", ["cfg2_small", "cfg4_ragged", "cfg3_small"])
-def test_two_rank_sharding_matches_reference(case, tmp_path):
+def test_two_rank_sharding_matches_reference(case, exchange, tmp_path):
+    """exchange = "p2p": the statistics row is summed by lvae_peer_sum_f64 over symmetric memory instead of NCCL."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from helpers import golden_hyper_vector, rel
-    mp.spawn(_worker, args=(2, 29700 + os.getpid() % 200, case, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29700 + os.getpid() % 200, case, str(tmp_path), exchange), nprocs=2, join=True)
     g = load_golden(case)
     outs = [torch.load(os.path.join(str(tmp_path), f"r{r}.pt"), weights_only=False) for r in range(2)]
     for o in outs:
@@ -64,3 +66,5 @@ def test_two_rank_sharding_matches_reference(case, tmp_path):
         assert np.abs(o["d_hyper"] - ref).max() <= 1e-6 * np.abs(ref).max()
         assert rel(o["d_mu"], g["d_mu"][o["lo"]:o["hi"]]) < 1e-6
     assert outs[0]["hi"] == outs[1]["lo"]
+    if exchange == "p2p":        # rank-ordered sums: the replicated tail gives bit-identical results on both ranks
+        assert outs[0]["kld"] == outs[1]["kld"] and torch.equal(outs[0]["gH"], outs[1]["gH"])
