@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
                     help="N > 1: statistics exchange by NCCL all-reduce or by the peer-memory kernel (symmetric memory)")
-    ap.add_argument("--latency-point", action="store_true", help="also time spb=20 (the reference's default batch)")
+    ap.add_argument("--no-latency-point", action="store_true", help="skip the spb=20 point (the reference's default batch)")
     return ap.parse_args()
 
 
@@ -457,7 +457,7 @@ def main():
     EF.set_process_group(None)
 
     lat = None
-    if args.latency_point and rank == 0 and world == 1:
+    if not args.no_latency_point and rank == 0 and world == 1 and P_b >= 20:
         spb2 = 20
         rows = int(b.offsets[spb2])
         off2 = offsets[:spb2 + 1].contiguous()
@@ -478,7 +478,29 @@ def main():
         for _ in range(50):
             small()
         b__.record(); torch.cuda.synchronize()
-        lat = {"spb": spb2, "ms_per_step": a_.elapsed_time(b__) / 50, "subjects_per_s": spb2 / (a_.elapsed_time(b__) / 50 * 1e-3)}
+        lat = {"spb": spb2, "ms_per_step": a_.elapsed_time(b__) / 50, "subjects_per_s": spb2 / (a_.elapsed_time(b__) / 50 * 1e-3),
+               "what": "spb = 20 (the reference's default minibatch), device-resident inputs, bound + gradients + NG update"}
+        try:      # the same step captured once into a CUDA graph (the C ABI is stream-ordered and capture-safe) and replayed
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                small()
+            torch.cuda.current_stream(device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                small()
+            for _ in range(5):
+                graph.replay()
+            torch.cuda.synchronize()
+            a_.record()
+            for _ in range(50):
+                graph.replay()
+            b__.record(); torch.cuda.synchronize()
+            lat["graph_ms_per_step"] = a_.elapsed_time(b__) / 50
+            lat["graph_subjects_per_s"] = spb2 / (a_.elapsed_time(b__) / 50 * 1e-3)
+            lat["graph_finite"] = bool(torch.isfinite(HH).all())
+        except Exception as ex:
+            lat["graph_unavailable"] = repr(ex)[:160]
 
     if rank == 0:
         cpu = None
