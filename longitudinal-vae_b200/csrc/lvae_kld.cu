@@ -38,7 +38,6 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.nh = p->ks.n_ls + p->ks.n_comp0 + p->ks.n_comp1 + 1;
     w.stride = stats_stride((int)M, w.nh);
     w.nchunk = lvae_chunks(p->P_b, p->L, p->T_max);
-    w.nprep = lvae_prep_rows(p->P_b, p->L, p->T_max, p->Q);
     int64_t o = 0;
     w.Ki = o; o += L * MM;
     w.Hi = o; o += L * MM;
@@ -52,6 +51,12 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.big = (p->path != 1) && lvae_big_supported(p) ? 1 : 0;
     w.MP = w.big ? (p->M <= 128 ? 128 : 256) : 0;
     w.v2 = (((p->path == 0 || p->path == 2) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
+    w.prep3 = (p->path != 1 && p->ks.spec && lvae_prep3_supported(p, w)) ? 1 : 0;
+    {
+        const char* e = getenv("LVAE_PREP");          // "2": force the second-generation prep kernel (A/B measurements)
+        if (e && e[0] == '2') w.prep3 = 0;
+    }
+    w.nprep = w.prep3 ? lvae_prep3_rows(p) : lvae_prep_rows(p->P_b, p->L, p->T_max, p->Q);
     w.nsplit = 1;
     if (w.big) {
         // CTAs per latent of the U/V and adjoint kernels: about two waves at 2 CTAs per SM
@@ -701,7 +706,10 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             prep_attr = s1;
         }
         lvae_prof_begin(1, st);
-        if (p->path != 1 && lvae_prep_warp_supported(p)) {
+        if (w.prep3) {
+            rc = lvae_prep3_launch(p, sp, w, st);
+            if (rc) return rc;
+        } else if (p->path != 1 && lvae_prep_warp_supported(p)) {
             rc = lvae_prep_warp_launch(p, sp, w, st);
             if (rc) return rc;
         } else {

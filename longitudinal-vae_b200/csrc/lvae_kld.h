@@ -24,6 +24,7 @@ struct KldLayout {
     int TP, gstride, v2;
     int nh, nchunk;                     // nchunk: CTAs per latent of the subject pass
     int nprep;                          // partial rows per latent of the prep pass
+    int prep3;                          // 1: third-generation prep kernel (lvae_prep3.cu)
     // 64 < M <= 256: GEMM-based path (lvae_kld_big.cu, lvae_subjects_big.cu); matrices padded to MP = 128 or 256
     int big, MP, nsplit;                // nsplit: k-splits of S = U^T U (rows of `part`); nchunk: CTAs per latent of k_uv / k_adj
     int64_t bF, bX, bInv, bT, bA0;      // [2L, MP*MP]: factors, triangular inverses, explicit inverses (Kzz | H), scratch, originals
@@ -64,3 +65,8 @@ int lvae_reduce_big_launch(const lvae_kld_problem_t* p, const KldLayout& w, cuda
 int64_t lvae_ng_big_workspace(int L, int M);
 int lvae_ng_big_launch(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hi, double lr, int L,
                        int M, double* ws, int32_t* info, cudaStream_t st);
+
+// third-generation prep kernel (lvae_prep3.cu)
+bool lvae_prep3_supported(const lvae_kld_problem_t* p, const KldLayout& w);
+int lvae_prep3_rows(const lvae_kld_problem_t* p);
+int lvae_prep3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
