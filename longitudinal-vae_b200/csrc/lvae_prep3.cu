@@ -278,9 +278,12 @@ __device__ __forceinline__ void grp_mm(const double* __restrict__ A, const doubl
     }
 }
 
+// rows allocated per matrix: T_max rounded up to 4 (tile rows beyond that only feed outputs that are never stored)
+template <int NT8, int LD>
+__host__ __device__ constexpr int rows3() { return LD < 8 * NT8 ? LD : 8 * NT8; }
 template <int NT8, int LD, int NW>
 __host__ __device__ constexpr int group_doubles3(int nslots_max) {
-    return 3 * (8 * NT8) * LD + nslots_max * LD + 3 * (8 * NT8) + 64 * NW + NW * (2 * NCM + 2);
+    return 3 * rows3<NT8, LD>() * LD + nslots_max * LD + 3 * (8 * NT8) + 64 * NW + NW * (2 * NCM + 2);
 }
 
 template <int NT8, int LD, int NW>
@@ -289,7 +292,8 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ mu,
         const double* __restrict__ log_v, const double* __restrict__ ls, const double* __restrict__ os,
         const double* __restrict__ noise, double c, double* __restrict__ d_log_v, double* __restrict__ ws, int32_t* info) {
-    constexpr int TP8 = 8 * NT8, NL = 32 * NW, TRI = TP8 * (TP8 + 1) / 2, KIT = (TRI + NL - 1) / NL, ASZ = TP8 * LD;
+    constexpr int TP8 = 8 * NT8, NL = 32 * NW, ROWS = rows3<NT8, LD>(), TRI = ROWS * (ROWS + 1) / 2, KIT = (TRI + NL - 1) / NL,
+                  ASZ = ROWS * LD;
     extern __shared__ double sm[];
     __shared__ PrepTab pt;
     __shared__ unsigned short ijt[TRI];
@@ -374,7 +378,7 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         }
         for (int t = gl; t < T; t += NL) sC -= 2.0 * log(dinv[t]);                                            // 192
         grp_tri_inverse<NT8, LD, NW>(A1, A2, T, dinv, tile, lane, wg, bar);
-        {   // rows of L^-1 for the subject pass: [row][k'], k' = column inside the subject, zero padded to TP
+        if (w.v2) {   // rows of L^-1 for the subject pass: [row][k'], k' = column inside the subject, zero padded to TP
             double* gl_ = ws + w.Lrows + ((size_t)l * N_b + r0) * w.TP;
             int i = 0, k = gl;
             while (k >= w.TP) { k -= w.TP; ++i; }
@@ -427,12 +431,21 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         gsync<NW>(bar);
         grp_mm<false, false, NT8, LD, NW>(A3, A2, A1, T, nt8, nk4, g, q, wg);                                   // X2 = B^-1 X1
         gsync<NW>(bar);
-        {
+        if (w.v2) {
             double* gb = ws + w.bmu + (size_t)l * N_b + r0;
             for (int t = gl; t < T; t += NL) {
                 double s = 0.0;
                 for (int k = 0; k < T; ++k) s += A3[t * LD + k] * mw[k];
                 gb[t] = s;
+            }
+        } else {      // first-generation fused / generic subject pass: the explicit inverse blocks
+            double* gBi = ws + w.Bi + (size_t)l * w.Bi_stride + reinterpret_cast<const int64_t*>(ws + w.off2)[p];
+            int i = 0, j = gl;
+            while (j >= T) { j -= T; ++i; }
+            for (int e = gl; e < T * T; e += NL) {
+                gBi[e] = A3[i * LD + j];
+                j += NL;
+                while (j >= T) { j -= T; ++i; }
             }
         }
         // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] against d K1 / d theta ; noise ; Bt ; d_log_v -----------------------
@@ -521,9 +534,12 @@ int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
 
 }  // namespace
 
-// third-generation prep kernel: fused / GEMM-based subject passes only (it exports L^-1 rows), <= 8 components, T <= 40
+// third-generation prep kernel: <= 8 components, T <= 24
 bool lvae_prep3_supported(const lvae_kld_problem_t* p, const KldLayout& w) {
-    return w.v2 && p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 40 && p->T_max >= 1;
+    (void)w;
+    // T <= 24 (one warp per task).  For 24 < T <= 40 the 4-warps-per-task instantiation of this kernel measured slower than
+    // k_prep_warp<4> of lvae_prep.cu (7.8 vs 4.7 ms at cfg4), so that range stays with the older kernel.
+    return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 24 && p->T_max >= 1;
 }
 
 // partial rows per latent (= warps per latent): about one wave of CTAs
@@ -532,8 +548,8 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
     for (int c_ = 0; c_ < p->ks.n_comp0 + p->ks.n_comp1; ++c_)
         ns += (p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE] >= 0) + p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE + 2];
     const int T = p->T_max;
-    const int nw = T <= 24 ? 1 : 4;
-    const int gpc = T <= 20 ? groups_per_cta3<3, 20, 1>(ns) : (T <= 24 ? groups_per_cta3<3, 28, 1>(ns) : groups_per_cta3<5, 44, 4>(ns));
+    const int nw = 1;
+    const int gpc = T <= 20 ? groups_per_cta3<3, 20, 1>(ns) : groups_per_cta3<3, 28, 1>(ns);
     const int pw = gpc * nw, per_sm = nw == 1 ? 2 : 1;
     int ctas = per_sm * 148 / p->L;
     if (ctas < 1) ctas = 1;
@@ -545,6 +561,5 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
 int lvae_prep3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int T = p->T_max;
     if (T <= 20) return launch3<3, 20, 1>(p, sp, w, st);
-    if (T <= 24) return launch3<3, 28, 1>(p, sp, w, st);
-    return launch3<5, 44, 4>(p, sp, w, st);
+    return launch3<3, 28, 1>(p, sp, w, st);
 }
