@@ -293,7 +293,8 @@ def main():
     offsets = torch.from_numpy(b.offsets).to(torch.int32).to(device)
     T_max, sum_T2 = int(Tl.max()), int((Tl * Tl).sum())
     const = L * (N_b * world) / 2 if ragged else L * P_tot * int(b.T) / 2
-    call = ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path)
+    call = (ops.make_kld_call(st, L, M, Q, Tl, device, natural_gradient=True, path=args.path) if ragged else
+            ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path))
     ng_ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=torch.float64, device=device)
     ng_info = torch.zeros(4, dtype=torch.int32, device=device)
     lr = 1e-3
@@ -325,7 +326,9 @@ def main():
     if args.path == 1:
         kernel_path = "generic"
     elif M <= 64:
-        kernel_path = "fused (one DMMA kernel per subject pass)" if T_max <= 24 or args.path == 2 else "fused v1"
+        kernel_path = ("fused (one DMMA kernel per subject pass)" if T_max <= 24 or args.path == 2 else
+                       "split: subjects with T <= 24 fused v2 + prep v3, longer ones fused v1 + 4-warp prep" if
+                       isinstance(call, ops.SplitKldCall) else "fused v1")
     else:
         kernel_path = "gemm (U/V materialised, S = U^T U and Y = V W as batched DMMA GEMMs)" if T_max <= 24 else "generic"
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)   # > 126 MB L2

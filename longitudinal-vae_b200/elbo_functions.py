@@ -75,8 +75,12 @@ class _KldBound(torch.autograd.Function):
         st = meta["structure"]
         x, z, offsets = meta["x"], meta["z"], meta["offsets"]
         L, M, Q = meta["L"], H.shape[-1], x.shape[1]
-        call = ops.KldCall(st, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"], meta["sum_T2"], x.device,
-                           natural_gradient=meta["natural_gradient"], path=_PATH)
+        if meta.get("counts") is not None:            # ragged minibatch: rows per subject known on the host
+            call = ops.make_kld_call(st, L, M, Q, meta["counts"], x.device, natural_gradient=meta["natural_gradient"],
+                                     path=_PATH)
+        else:
+            call = ops.KldCall(st, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"], meta["sum_T2"], x.device,
+                               natural_gradient=meta["natural_gradient"], path=_PATH)
         call.bind(x, offsets, mu, log_v, z, m.reshape(L, M), H, lengthscale, outputscale, noise, meta["scale"],
                   meta["const_term"], meta["eps"])
         call.head()
@@ -112,7 +116,7 @@ def _structure_of(covar_module0, covar_module1, L, device):
 
 
 def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets, T_max, sum_T2, mu, log_v, z, scale,
-         const_term, natural_gradient, eps):
+         const_term, natural_gradient, eps, counts=None):
     if not x.is_cuda:
         raise RuntimeError("lvae_b200: the GP-prior ELBO op needs CUDA tensors (no CPU fallback)")
     L = latent_dim
@@ -122,7 +126,7 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
     if z.dim() == 2:
         z = z.unsqueeze(0).expand(L, -1, -1)
     meta = dict(structure=st, x=x.to(f64), z=z.to(f64), offsets=offsets, L=L, T_max=int(T_max), sum_T2=int(sum_T2),
-                scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient))
+                scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient), counts=counts)
     kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), ls, os_, noise, meta)
     if natural_gradient:
         gH._lvae_hinv = meta.get("Hinv")
@@ -155,6 +159,7 @@ def group_by_subject(ids):
     offsets = torch.zeros(counts_h.numel() + 1, dtype=torch.int64)
     torch.cumsum(counts_h, 0, out=offsets[1:])
     grouped = bool((order == torch.arange(order.numel(), device=order.device)).all())
+    group_by_subject.last_counts = counts_h.numpy()
     return (None if grouped else order, offsets.to(torch.int32).to(ids.device), int(counts_h.max()),
             int((counts_h * counts_h).sum()))
 
@@ -167,7 +172,8 @@ def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, lat
     if order is not None:
         train_xt, mu, log_v = train_xt[order], mu[order], log_v[order]
     kld, gm, gH = _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, offsets, T_max, sum_T2, mu,
-                       log_v, z, P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps)
+                       log_v, z, P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps,
+                       counts=group_by_subject.last_counts)
     return kld.reshape(1), gm, gH
 
 

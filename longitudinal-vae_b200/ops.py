@@ -168,6 +168,84 @@ class KldCall:
                 raise RuntimeError(f"cholesky: {n} is not positive-definite (flat index {v - 1})")
 
 
+class SplitKldCall:
+    """Ragged minibatches with M <= 64 whose longest subject has more than 24 rows: the subjects with at most 24 rows go
+    through the fast kernels (third-generation prep + second-generation fused subject pass), the others through the
+    T <= 40 kernels; both passes write their own statistics row, the rows are added (every batch-dependent statistic is a sum
+    over subjects) and ONE tail runs.  Same interface as KldCall; d_mu / d_log_v come back in the caller's row order."""
+
+    def __init__(self, structure, L, M, Q, counts, device, natural_gradient=True, path=0):
+        counts = np.asarray(counts, dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(counts)])
+        self.device, self.L, self.M, self.N_b = torch.device(device), L, M, int(off[-1])
+        self.parts = []
+        for sel in (counts <= 24, counts > 24):
+            idx = np.nonzero(sel)[0]
+            c = counts[idx]
+            start = np.cumsum(c) - c                                      # first local row of every selected subject
+            rows = np.repeat(off[idx] - start, c) + np.arange(int(c.sum()))   # global row of every local row
+            call = KldCall(structure, L, M, Q, len(idx), int(c.sum()), int(c.max()), int((c * c).sum()), device,
+                           natural_gradient, path)
+            offs = torch.from_numpy(np.concatenate([[0], np.cumsum(c)]).astype(np.int32)).to(self.device)
+            self.parts.append((call, torch.from_numpy(rows).to(self.device), offs))
+        a = self.parts[0][0]
+        self.kld_per_latent, self.grad_m, self.grad_H = a.kld_per_latent, a.grad_m, a.grad_H
+        self.d_lengthscale, self.d_outputscale, self.d_noise = a.d_lengthscale, a.d_outputscale, a.d_noise
+        self.stats, self.Hinv, self.info = a.stats, a.Hinv, a.info
+        self.d_mu = torch.empty(self.N_b, L, dtype=F64, device=self.device)
+        self.d_log_v = torch.empty(self.N_b, L, dtype=F64, device=self.device)
+        self._target = self.stats
+
+    def bind(self, x, offsets_dev, mu, log_v, z, m, H, lengthscale, outputscale, noise, scale, const_term, eps):
+        for call, rows, offs in self.parts:
+            call.bind(x[rows], offs, mu[rows], log_v[rows], z, m, H, lengthscale, outputscale, noise, scale, const_term, eps)
+        return self
+
+    def set_stats(self, t):
+        self._target = t
+
+    def head(self):
+        for call, _, _ in self.parts:
+            call.head()
+
+    def subjects(self):
+        (a, _, _), (b, _, _) = self.parts
+        a.subjects()
+        b.subjects()
+        torch.add(a.stats, b.stats, out=self._target.view_as(a.stats) if self._target.numel() == a.stats.numel()
+                  else self._target[:a.stats.numel()].view_as(a.stats))
+
+    def tail(self):
+        (a, ra, _), (b, rb, _) = self.parts
+        a.tail()
+        self.d_mu[ra], self.d_mu[rb] = a.d_mu, b.d_mu
+        self.d_log_v[ra], self.d_log_v[rb] = a.d_log_v, b.d_log_v
+
+    def run(self):
+        self.head()
+        self.subjects()
+        self.tail()
+
+    def post_info(self):
+        for call, _, _ in self.parts:
+            call.post_info()
+
+    def raise_on_info(self):
+        for call, _, _ in self.parts:
+            call.raise_on_info()
+
+
+def make_kld_call(structure, L, M, Q, counts, device, natural_gradient=True, path=0):
+    """KldCall for a minibatch whose subjects have `counts` rows (host array), or SplitKldCall when that is faster."""
+    counts = np.asarray(counts, dtype=np.int64)
+    if path == 0 and M <= 64 and counts.size and counts.max() > 24:
+        short = counts <= 24
+        if short.any() and counts[short].sum() >= 0.1 * counts.sum():
+            return SplitKldCall(structure, L, M, Q, counts, device, natural_gradient, path)
+    return KldCall(structure, L, M, Q, counts.size, int(counts.sum()), int(counts.max()) if counts.size else 0,
+                   int((counts * counts).sum()), device, natural_gradient, path)
+
+
 def ng_step(m, H, grad_m, grad_H, lr, Hinv=None):
     """Natural-gradient update of (m [L,M,1], H [L,M,M]) — training.py:129-135.  Returns new detached tensors.
     Hinv: H^-1 already computed by the bound's head kernel for this H (saves one Cholesky + inverse)."""

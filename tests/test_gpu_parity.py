@@ -25,8 +25,8 @@ def test_bound_and_gradients_vs_reference_golden(name, path):
     g = load_golden(name)
     if path == 2 and g["H"].shape[-1] > 64:
         pytest.skip("fused DMMA kernel covers M <= 64")
-    if path == 0 and g["H"].shape[-1] <= 64:
-        pytest.skip("auto == fused for M <= 64 (covered by path 2)")
+    if path == 0 and g["H"].shape[-1] <= 64 and not bool(g["ragged"]):
+        pytest.skip("auto == fused for M <= 64 (covered by path 2); ragged: auto may split the subjects by length")
     out = run_cuda_case(g, path=path)
     assert abs(out["kld"] - float(g["kld"])) <= TOL * abs(float(g["kld"]))
     assert rel(out["d_mu"], g["d_mu"]) < TOL
