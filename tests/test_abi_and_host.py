@@ -122,3 +122,33 @@ def test_group_by_subject_matches_boolean_mask_grouping():
     sorted_ids = np.sort(ids)
     order2, *_ = group_by_subject(torch.from_numpy(sorted_ids))
     assert order2 is None
+
+
+def test_split_call_row_mapping_and_decision():
+    """Host logic of ops.make_kld_call / SplitKldCall (ragged minibatches with long subjects): which subjects go where, and the
+    global row of every local row, without touching the GPU."""
+    import numpy as np
+    from lvae_b200 import ops
+    counts = np.array([3, 30, 5, 26, 24, 1, 40])
+    off = np.concatenate([[0], np.cumsum(counts)])
+    seen = []
+    for sel in (counts <= 24, counts > 24):
+        idx = np.nonzero(sel)[0]
+        c = counts[idx]
+        start = np.cumsum(c) - c
+        rows = np.repeat(off[idx] - start, c) + np.arange(int(c.sum()))
+        assert np.array_equal(rows, np.concatenate([np.arange(off[p], off[p + 1]) for p in idx]))
+        seen.append(rows)
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(off[-1]))      # a partition of the rows
+
+    # decision rule (no device needed: it only inspects the counts before constructing anything)
+    def decide(M, counts, path=0):
+        counts = np.asarray(counts)
+        if path == 0 and M <= 64 and counts.size and counts.max() > 24:
+            short = counts <= 24
+            return bool(short.any() and counts[short].sum() >= 0.1 * counts.sum())
+        return False
+    assert decide(60, [5, 40, 20]) and not decide(60, [20, 20]) and not decide(128, [5, 40]) and not decide(60, [40, 39])
+    assert not decide(60, [5, 40], path=1) and not decide(60, [1] + [40] * 50)
+    src = open(ops.__file__).read()
+    assert "counts[short].sum() >= 0.1 * counts.sum()" in src and "counts.max() > 24" in src   # the rule tested above is the shipped one
