@@ -12,6 +12,8 @@
 //   B_p = K1(X_p, X_p) + s2 I -> Cholesky -> L^-1 -> B_p^-1 (elbo_functions.py:174,179-180); K0_p (173); C, D1, Bt, F
 //   (191-196); d_log_v; local adjoints c B^-1 (of K0_p) and c (B^-1 - B^-1 (diag v + K0_p) B^-1) (of B_p) contracted
 //   with d k_c / d theta; exports the rows of L_p^-1 and B_p^-1 mu_p for the subject pass.
+#include <stdlib.h>
+
 #include "lvae_kld.h"
 
 namespace {
@@ -87,6 +89,61 @@ __device__ __forceinline__ double eval_rr(const double* __restrict__ X, int i, i
         e = exp_neg(d2 * negh, etab);
     }
     return on ? e : 0.0;
+}
+
+// fn(i, j, f, d2) for every lower-triangle entry (i, j) of this lane (entries gl, gl + NL, ... < ntri through the (i, j)
+// table), component c.  The entry loops stay ROLLED: one body per shape and call site keeps the kernel small — the first,
+// fully unrolled version of these loops stalled on instruction fetch (ncu: no_instruction 10 cycles per issue) as soon as the
+// warps of an SM worked on subjects of different lengths.
+template <int LDX, class Fn>
+__device__ __forceinline__ void eval_tri(const PrepTab& pt, int c, const double* __restrict__ XC,
+                                         const unsigned short* __restrict__ ijt, int gl, int nl, int ntri, Fn&& fn) {
+    const double* X = XC + pt.slot0[c] * LDX;
+    const double negh = pt.negh[c];
+    const int nm = pt.nmask[c];
+    const bool rbf = pt.rbf[c] != 0;
+    double sgn[3], tgt[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { sgn[m] = pt.sgn[c][m]; tgt[m] = pt.tgt[c][m]; }
+    double d2;
+    if (nm == 0) {
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += nl) {
+            const int v = ijt[e], i = v & 255, j = v >> 8;
+            const double f = eval_rr<0, true, LDX>(X, i, j, sgn, tgt, negh, pt.etab, d2);
+            fn(i, j, f, d2);
+        }
+    } else if (nm == 1 && rbf) {
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += nl) {
+            const int v = ijt[e], i = v & 255, j = v >> 8;
+            const double f = eval_rr<1, true, LDX>(X, i, j, sgn, tgt, negh, pt.etab, d2);
+            fn(i, j, f, d2);
+        }
+    } else if (nm == 1) {
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += nl) {
+            const int v = ijt[e], i = v & 255, j = v >> 8;
+            const double f = eval_rr<1, false, LDX>(X, i, j, sgn, tgt, negh, pt.etab, d2);
+            fn(i, j, f, d2);
+        }
+    } else {                                   // 2-3 factors: run-time factor loop
+        const int o = rbf ? 1 : 0;
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += nl) {
+            const int v = ijt[e], i = v & 255, j = v >> 8;
+            bool on = true;
+            for (int m = 0; m < nm; ++m) on = on && (fma(pt.sgn[c][m], X[(o + m) * LDX + j], X[(o + m) * LDX + i]) == pt.tgt[c][m]);
+            double ex = 1.0;
+            d2 = 0.0;
+            if (rbf) {
+                const double t = X[i] - X[j];
+                d2 = t * t;
+                ex = exp_neg(d2 * negh, pt.etab);
+            }
+            fn(i, j, on ? ex : 0.0, d2);
+        }
+    }
 }
 
 // fn(k, f, d2) for every triangle entry k < KIT of this lane (ij[k] = i | j << 8, ij < 0: none), component c
@@ -286,14 +343,16 @@ __host__ __device__ constexpr int group_doubles3(int nslots_max) {
     return 3 * rows3<NT8, LD>() * LD + nslots_max * LD + 3 * (8 * NT8) + 64 * NW + NW * (2 * NCM + 2);
 }
 
-template <int NT8, int LD, int NW>
+// UNR: every subject of the batch has the same number of rows -> the entry loops are fully unrolled with the (i, j) pairs in
+// registers (fastest when all warps run in step); otherwise they stay rolled (see eval_tri).
+template <int NT8, int LD, int NW, bool UNR>
 __global__ void __launch_bounds__(NW == 1 ? 256 : 512, NW == 1 ? 2 : 1)
 k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int N_b, int nslots_max,
         const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ mu,
         const double* __restrict__ log_v, const double* __restrict__ ls, const double* __restrict__ os,
         const double* __restrict__ noise, double c, double* __restrict__ d_log_v, double* __restrict__ ws, int32_t* info) {
-    constexpr int TP8 = 8 * NT8, NL = 32 * NW, ROWS = rows3<NT8, LD>(), TRI = ROWS * (ROWS + 1) / 2, KIT = (TRI + NL - 1) / NL,
-                  ASZ = ROWS * LD;
+    constexpr int TP8 = 8 * NT8, NL = 32 * NW, ROWS = rows3<NT8, LD>(), TRI = ROWS * (ROWS + 1) / 2, ASZ = ROWS * LD,
+                  KIT = UNR ? (TRI + NL - 1) / NL : 1;
     extern __shared__ double sm[];
     __shared__ PrepTab pt;
     __shared__ unsigned short ijt[TRI];
@@ -344,30 +403,48 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
             sF += lv;
             mw[t] = mu[(size_t)(r0 + t) * L + l];
         }
-        int ij[KIT];
+        int ij[KIT];      // (i | j << 8) of this lane's entries (UNR only)
 #pragma unroll
         for (int k = 0; k < KIT; ++k) {
             const int e = gl + k * NL;
             ij[k] = e < ntri ? (int)ijt[e < TRI ? e : 0] : -1;
         }
         gsync<NW>(bar);
-        // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) ; A2 <- 0 -----------------------------------------------
-        {
-            double kv[KIT];
-#pragma unroll
-            for (int k = 0; k < KIT; ++k) kv[k] = 0.0;
+        if constexpr (UNR) {
+            // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) ; A2 <- 0 -----------------------------------------------
+            {
+                double kv[KIT];
+    #pragma unroll
+                for (int k = 0; k < KIT; ++k) kv[k] = 0.0;
+                for (int cc = sp.n0; cc < nc; ++cc) {
+                    const double o = pt.osc[cc];
+                    eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double) { kv[k] += o * f; });
+                }
+    #pragma unroll
+                for (int k = 0; k < KIT; ++k) {
+                    if (ij[k] >= 0) {
+                        const int i = ij[k] & 255, j = ij[k] >> 8;
+                        const double v = kv[k] + (i == j ? pt.noise : 0.0);
+                        A1[i * LD + j] = v;
+                        A1[j * LD + i] = v;
+                    }
+                }
+            }
+        } else {
+            // ---- B_p = K1 + noise I: every lane accumulates ITS lower-triangle entries in place over the components, then mirrors ----
             for (int cc = sp.n0; cc < nc; ++cc) {
                 const double o = pt.osc[cc];
-                eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double) { kv[k] += o * f; });
+                const bool first = cc == sp.n0;
+                eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double) {
+                    A1[i * LD + j] = (first ? 0.0 : A1[i * LD + j]) + o * f;
+                });
             }
-#pragma unroll
-            for (int k = 0; k < KIT; ++k) {
-                if (ij[k] >= 0) {
-                    const int i = ij[k] & 255, j = ij[k] >> 8;
-                    const double v = kv[k] + (i == j ? pt.noise : 0.0);
-                    A1[i * LD + j] = v;
-                    A1[j * LD + i] = v;
-                }
+    #pragma unroll 1
+            for (int e = gl; e < ntri; e += NL) {
+                const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
+                const double v = A1[i * LD + j] + (i == j ? pt.noise : 0.0);
+                A1[i * LD + j] = v;
+                A1[j * LD + i] = v;
             }
         }
         for (int e = gl; e < ASZ; e += NL) A2[e] = 0.0;
@@ -390,24 +467,52 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         }
         grp_mm<true, true, NT8, LD, NW>(A2, A2, A3, T, nt8, nk4, g, q, wg);                                     // B^-1 = L^-T L^-1
         gsync<NW>(bar);
-        // ---- K0_p (+ diag v) into A1 ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta ---------------------------------------
-        {
-            double kv[KIT], bi[KIT];
-#pragma unroll
-            for (int k = 0; k < KIT; ++k) {
-                kv[k] = 0.0;
-                bi[k] = 0.0;
-                if (ij[k] >= 0) {
-                    const int i = ij[k] & 255, j = ij[k] >> 8;
-                    bi[k] = A3[i * LD + j] * (i == j ? 1.0 : 2.0);
+        if constexpr (UNR) {
+            // ---- K0_p (+ diag v) into A1 ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta ---------------------------------------
+            {
+                double kv[KIT], bi[KIT];
+    #pragma unroll
+                for (int k = 0; k < KIT; ++k) {
+                    kv[k] = 0.0;
+                    bi[k] = 0.0;
+                    if (ij[k] >= 0) {
+                        const int i = ij[k] & 255, j = ij[k] >> 8;
+                        bi[k] = A3[i * LD + j] * (i == j ? 1.0 : 2.0);
+                    }
+                }
+                for (int cc = 0; cc < sp.n0; ++cc) {
+                    const double o = pt.osc[cc];
+                    double s1 = 0.0, s2 = 0.0;
+                    eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double d2) {
+                        kv[k] += o * f;
+                        const double w_ = bi[k] * f;
+                        s1 += w_;
+                        s2 += w_ * d2;
+                    });
+                    s1 = warp_sum(s1);
+                    s2 = warp_sum(s2);
+                    if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
+                }
+    #pragma unroll
+                for (int k = 0; k < KIT; ++k) {
+                    if (ij[k] >= 0) {
+                        const int i = ij[k] & 255, j = ij[k] >> 8;
+                        sD1 += bi[k] * kv[k];
+                        const double v = kv[k] + (i == j ? ev[i] : 0.0);
+                        A1[i * LD + j] = v;
+                        A1[j * LD + i] = v;
+                    }
                 }
             }
+        } else {
+            // ---- K0_p (+ diag v) into A1 (accumulated in place over the components) ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta
             for (int cc = 0; cc < sp.n0; ++cc) {
                 const double o = pt.osc[cc];
+                const bool first = cc == 0;
                 double s1 = 0.0, s2 = 0.0;
-                eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double d2) {
-                    kv[k] += o * f;
-                    const double w_ = bi[k] * f;
+                eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double d2) {
+                    A1[i * LD + j] = (first ? 0.0 : A1[i * LD + j]) + o * f;
+                    const double w_ = A3[i * LD + j] * (i == j ? 1.0 : 2.0) * f;
                     s1 += w_;
                     s2 += w_ * d2;
                 });
@@ -415,15 +520,14 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
                 s2 = warp_sum(s2);
                 if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
             }
-#pragma unroll
-            for (int k = 0; k < KIT; ++k) {
-                if (ij[k] >= 0) {
-                    const int i = ij[k] & 255, j = ij[k] >> 8;
-                    sD1 += bi[k] * kv[k];
-                    const double v = kv[k] + (i == j ? ev[i] : 0.0);
-                    A1[i * LD + j] = v;
-                    A1[j * LD + i] = v;
-                }
+    #pragma unroll 1
+            for (int e = gl; e < ntri; e += NL) {
+                const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
+                const double k0 = A1[i * LD + j];
+                sD1 += A3[i * LD + j] * (i == j ? 1.0 : 2.0) * k0;
+                const double v = k0 + (i == j ? ev[i] : 0.0);
+                A1[i * LD + j] = v;
+                A1[j * LD + i] = v;
             }
         }
         gsync<NW>(bar);
@@ -448,30 +552,61 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
                 while (j >= T) { j -= T; ++i; }
             }
         }
-        // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] against d K1 / d theta ; noise ; Bt ; d_log_v -----------------------
-        {
-            double gB[KIT];
-#pragma unroll
-            for (int k = 0; k < KIT; ++k) {
-                gB[k] = 0.0;
-                if (ij[k] >= 0) {
-                    const int i = ij[k] & 255, j = ij[k] >> 8;
-                    const double b_ = A3[i * LD + j];
-                    if (i == j) {
-                        gB[k] = b_ - A1[i * LD + i];
-                        gno += gB[k];
-                        const double bt = b_ * ev[i];
-                        sBt += bt;
-                        d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
-                    } else {
-                        gB[k] = 2.0 * b_ - (A1[i * LD + j] + A1[j * LD + i]);
+        if constexpr (UNR) {
+            // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] against d K1 / d theta ; noise ; Bt ; d_log_v -----------------------
+            {
+                double gB[KIT];
+    #pragma unroll
+                for (int k = 0; k < KIT; ++k) {
+                    gB[k] = 0.0;
+                    if (ij[k] >= 0) {
+                        const int i = ij[k] & 255, j = ij[k] >> 8;
+                        const double b_ = A3[i * LD + j];
+                        if (i == j) {
+                            gB[k] = b_ - A1[i * LD + i];
+                            gno += gB[k];
+                            const double bt = b_ * ev[i];
+                            sBt += bt;
+                            d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
+                        } else {
+                            gB[k] = 2.0 * b_ - (A1[i * LD + j] + A1[j * LD + i]);
+                        }
                     }
                 }
+                for (int cc = sp.n0; cc < nc; ++cc) {
+                    double s1 = 0.0, s2 = 0.0;
+                    eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double d2) {
+                        const double w_ = gB[k] * f;
+                        s1 += w_;
+                        s2 += w_ * d2;
+                    });
+                    s1 = warp_sum(s1);
+                    s2 = warp_sum(s2);
+                    if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
+                }
+            }
+            } else {
+            // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] -> A2 (X1 is dead), then against d K1 / d theta ; noise ; Bt ; d_log_v
+    #pragma unroll 1
+            for (int e = gl; e < ntri; e += NL) {
+                const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
+                const double b_ = A3[i * LD + j];
+                double gB;
+                if (i == j) {
+                    gB = b_ - A1[i * LD + i];
+                    gno += gB;
+                    const double bt = b_ * ev[i];
+                    sBt += bt;
+                    d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
+                } else {
+                    gB = 2.0 * b_ - (A1[i * LD + j] + A1[j * LD + i]);
+                }
+                A2[i * LD + j] = gB;
             }
             for (int cc = sp.n0; cc < nc; ++cc) {
                 double s1 = 0.0, s2 = 0.0;
-                eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double d2) {
-                    const double w_ = gB[k] * f;
+                eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double d2) {
+                    const double w_ = A2[i * LD + j] * f;
                     s1 += w_;
                     s2 += w_ * d2;
                 });
@@ -479,7 +614,7 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
                 s2 = warp_sum(s2);
                 if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
             }
-        }
+            }
     }
     // ---- one partial row per warp (summed in fixed order by the reduce kernel) ------------------------------------------------
     __syncwarp();
@@ -512,19 +647,19 @@ int groups_per_cta3(int nslots) {
     return n < 1 ? 1 : n;
 }
 
-template <int NT8, int LD, int NW>
+template <int NT8, int LD, int NW, bool UNR>
 int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int nslots = slots_of(sp);
     const int gpc = groups_per_cta3<NT8, LD, NW>(nslots), pw = gpc * NW;
     const size_t smem = sizeof(double) * (size_t)gpc * group_doubles3<NT8, LD, NW>(nslots);
     static size_t attr = 0;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_prep3<NT8, LD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_prep3<NT8, LD, NW, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         attr = smem;
     }
     if (w.nprep % pw != 0) return LVAE_E_BADARG;
-    k_prep3<NT8, LD, NW><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, nslots, p->x, p->offsets,
+    k_prep3<NT8, LD, NW, UNR><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, nslots, p->x, p->offsets,
                                                                           p->mu, p->log_v, p->lengthscale, p->outputscale,
                                                                           p->noise, 0.5 * p->scale, p->d_log_v, p->workspace,
                                                                           p->info);
@@ -537,6 +672,10 @@ int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
 // third-generation prep kernel: <= 8 components, T <= 24
 bool lvae_prep3_supported(const lvae_kld_problem_t* p, const KldLayout& w) {
     (void)w;
+    {
+        const char* e = getenv("LVAE_PREP3_LONG");       // measurement switch: also take 24 < T <= 40 (4 warps per task)
+        if (e && e[0] == '1') return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 40 && p->T_max >= 1;
+    }
     // T <= 24 (one warp per task).  For 24 < T <= 40 the 4-warps-per-task instantiation of this kernel measured slower than
     // k_prep_warp<4> of lvae_prep.cu (7.8 vs 4.7 ms at cfg4), so that range stays with the older kernel.
     return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 24 && p->T_max >= 1;
@@ -548,8 +687,8 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
     for (int c_ = 0; c_ < p->ks.n_comp0 + p->ks.n_comp1; ++c_)
         ns += (p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE] >= 0) + p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE + 2];
     const int T = p->T_max;
-    const int nw = 1;
-    const int gpc = T <= 20 ? groups_per_cta3<3, 20, 1>(ns) : groups_per_cta3<3, 28, 1>(ns);
+    const int nw = T <= 24 ? 1 : 4;
+    const int gpc = T <= 20 ? groups_per_cta3<3, 20, 1>(ns) : (T <= 24 ? groups_per_cta3<3, 28, 1>(ns) : groups_per_cta3<5, 44, 4>(ns));
     const int pw = gpc * nw, per_sm = nw == 1 ? 2 : 1;
     int ctas = per_sm * 148 / p->L;
     if (ctas < 1) ctas = 1;
@@ -560,6 +699,8 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
 
 int lvae_prep3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int T = p->T_max;
-    if (T <= 20) return launch3<3, 20, 1>(p, sp, w, st);
-    return launch3<3, 28, 1>(p, sp, w, st);
+    const bool uniform = p->sum_T2 == (int64_t)p->P_b * T * T;      // every subject has exactly T_max rows
+    if (T <= 20) return uniform ? launch3<3, 20, 1, true>(p, sp, w, st) : launch3<3, 20, 1, false>(p, sp, w, st);
+    if (T <= 24) return uniform ? launch3<3, 28, 1, true>(p, sp, w, st) : launch3<3, 28, 1, false>(p, sp, w, st);
+    return launch3<5, 44, 4, false>(p, sp, w, st);
 }
