@@ -2,11 +2,14 @@
 // lvae_prep.cu, which stays as the fallback for kernel shapes this one does not cover).  The profile of the previous
 // version was flat and 86 % integer / control instructions (ncu, profiles/r01_cfg2_prep_fused2_ncu_summary.txt), so this
 // one removes them structurally:
-//   * NT8 (8-row tiles per matrix), the row stride LD and NW (warps per task) are compile-time: tile loops unroll, every
-//     shared-memory address is base + constant;
+//   * NT8 (8-row tiles per matrix), the row stride LD and NW (warps per task) are compile-time: every shared-memory address
+//     is base + constant; the tile loops of the T x T linear algebra are unrolled for 3 x 3 tiles only (for 5 x 5 the code
+//     outgrows the instruction cache: measured 2.9 -> 1.8 ms at cfg4 when they were rolled again);
 //   * the lower triangle is walked through a (i, j) table built once per CTA instead of incremental index arithmetic;
 //   * covariates are gathered per component once per task, and every component is evaluated by straight-line code
 //     selected by a warp-uniform switch on its shape (SE | cat/bin x SE | cat/bin | generic), hoisted out of the entry loop;
+//     the entry loops themselves stay rolled and accumulate in place in shared memory (a fully unrolled variant with the
+//     entries in registers was 10 % slower at fixed T and 3x slower on ragged batches: instruction-fetch stalls);
 //   * hyper-gradient partial sums are reduced per component (warp shuffle) into a per-warp shared-memory row instead
 //     of per-lane register arrays indexed by a run-time component number.
 //   B_p = K1(X_p, X_p) + s2 I -> Cholesky -> L^-1 -> B_p^-1 (elbo_functions.py:174,179-180); K0_p (173); C, D1, Bt, F
@@ -146,51 +149,8 @@ __device__ __forceinline__ void eval_tri(const PrepTab& pt, int c, const double*
     }
 }
 
-// fn(k, f, d2) for every triangle entry k < KIT of this lane (ij[k] = i | j << 8, ij < 0: none), component c
-template <int KIT, int LDX, class Fn>
-__device__ __forceinline__ void eval_entries(const PrepTab& pt, int c, const double* __restrict__ XC, const int (&ij)[KIT], Fn&& fn) {
-    const double* X = XC + pt.slot0[c] * LDX;
-    const double negh = pt.negh[c];
-    const int nm = pt.nmask[c];
-    const bool rbf = pt.rbf[c] != 0;
-    double sgn[3], tgt[3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) { sgn[m] = pt.sgn[c][m]; tgt[m] = pt.tgt[c][m]; }
-    double d2;
-    if (nm == 0) {
-#pragma unroll
-        for (int k = 0; k < KIT; ++k)
-            if (ij[k] >= 0) { const double f = eval_rr<0, true, LDX>(X, ij[k] & 255, ij[k] >> 8, sgn, tgt, negh, pt.etab, d2); fn(k, f, d2); }
-    } else if (nm == 1 && rbf) {
-#pragma unroll
-        for (int k = 0; k < KIT; ++k)
-            if (ij[k] >= 0) { const double f = eval_rr<1, true, LDX>(X, ij[k] & 255, ij[k] >> 8, sgn, tgt, negh, pt.etab, d2); fn(k, f, d2); }
-    } else if (nm == 1) {
-#pragma unroll
-        for (int k = 0; k < KIT; ++k)
-            if (ij[k] >= 0) { const double f = eval_rr<1, false, LDX>(X, ij[k] & 255, ij[k] >> 8, sgn, tgt, negh, pt.etab, d2); fn(k, f, d2); }
-    } else {                                   // 2-3 factors: run-time factor loop
-#pragma unroll
-        for (int k = 0; k < KIT; ++k) {
-            if (ij[k] >= 0) {
-                const int i = ij[k] & 255, j = ij[k] >> 8, o = rbf ? 1 : 0;
-                bool on = true;
-                for (int m = 0; m < nm; ++m) on = on && (fma(sgn[m], X[(o + m) * LDX + j], X[(o + m) * LDX + i]) == tgt[m]);
-                double e = 1.0;
-                d2 = 0.0;
-                if (rbf) {
-                    const double t = X[i] - X[j];
-                    d2 = t * t;
-                    e = exp_neg(d2 * negh, pt.etab);
-                }
-                fn(k, on ? e : 0.0, d2);
-            }
-        }
-    }
-}
-
 // ---- linear algebra on T x T matrices in shared memory, compile-time stride LD and tile count NT8 ------------------------------
-template <int NT8, int LD, int NW>
+template <int NT8, int LD, int NW, bool TU>
 __device__ __forceinline__ int grp_cholesky(double* __restrict__ A, int T, double* __restrict__ dinv, int lane, int wg, int bar) {
     const int g = lane >> 2, q = lane & 3, gl = lane + 32 * wg;
     const int nb = (T + 7) >> 3;
@@ -199,7 +159,7 @@ __device__ __forceinline__ int grp_cholesky(double* __restrict__ A, int T, doubl
     while ((ur + 1) * (ur + 2) / 2 <= lane) ++ur;
     const int uc = lane - ur * (ur + 1) / 2 + 1;
     ur += 1;
-#pragma unroll
+#pragma unroll(TU ? NT8 : 1)
     for (int kb = 0; kb < NT8; ++kb) {
         if (kb < nb) {
             const int k0 = 8 * kb, bs = min(8, T - k0);
@@ -234,9 +194,9 @@ __device__ __forceinline__ int grp_cholesky(double* __restrict__ A, int T, doubl
                 }
                 gsync<NW>(bar);
                 int tl = 0;
-#pragma unroll
+#pragma unroll(TU ? NT8 : 1)
                 for (int ti = kb + 1; ti < NT8; ++ti) {
-#pragma unroll
+#pragma unroll(TU ? NT8 : 1)
                     for (int tj = kb + 1; tj <= ti; ++tj, ++tl) {
                         if (ti < nb && (NW == 1 || (tl % NW) == wg)) {
                             const int i = 8 * ti + g, j = 8 * tj + 2 * q;
@@ -257,7 +217,7 @@ __device__ __forceinline__ int grp_cholesky(double* __restrict__ A, int T, doubl
     return bad;
 }
 
-template <int NT8, int LD, int NW>
+template <int NT8, int LD, int NW, bool TU>
 __device__ __forceinline__ void grp_tri_inverse(const double* __restrict__ Lc, double* __restrict__ X, int T,
                                                 const double* __restrict__ dinv, double* __restrict__ tile, int lane, int wg,
                                                 int bar) {
@@ -273,7 +233,7 @@ __device__ __forceinline__ void grp_tri_inverse(const double* __restrict__ Lc, d
         }
     }
     gsync<NW>(bar);
-#pragma unroll
+#pragma unroll(TU ? NT8 : 1)
     for (int d = 1; d < NT8; ++d) {
         if (d < nb) {
             for (int bj = wg; bj + d < nb; bj += NW) {
@@ -301,10 +261,10 @@ __device__ __forceinline__ void grp_tri_inverse(const double* __restrict__ Lc, d
 }
 
 // C = op(A) B on the T x T leading blocks (TA: op(A)(i,k) = A[k][i]; SYM: lower tiles only, mirrored); rows of tiles dealt to warps
-template <bool TA, bool SYM, int NT8, int LD, int NW>
+template <bool TA, bool SYM, int NT8, int LD, int NW, bool TU>
 __device__ __forceinline__ void grp_mm(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int T,
                                        int nt8, int nk4, int g, int q, int wg) {
-#pragma unroll
+#pragma unroll(TU ? NT8 : 1)
     for (int ti = 0; ti < NT8; ++ti) {
         if (ti < nt8 && (NW == 1 || (ti % NW) == wg)) {
             double acc[NT8][2];
@@ -343,16 +303,14 @@ __host__ __device__ constexpr int group_doubles3(int nslots_max) {
     return 3 * rows3<NT8, LD>() * LD + nslots_max * LD + 3 * (8 * NT8) + 64 * NW + NW * (2 * NCM + 2);
 }
 
-// UNR: every subject of the batch has the same number of rows -> the entry loops are fully unrolled with the (i, j) pairs in
-// registers (fastest when all warps run in step); otherwise they stay rolled (see eval_tri).
-template <int NT8, int LD, int NW, bool UNR>
+// TU: unroll the tile loops of the T x T linear algebra (pays for 3 x 3 tiles, not for 5 x 5: code size)
+template <int NT8, int LD, int NW, bool TU>
 __global__ void __launch_bounds__(NW == 1 ? 256 : 512, NW == 1 ? 2 : 1)
 k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int Q, int P_b, int N_b, int nslots_max,
         const double* __restrict__ x, const int32_t* __restrict__ offsets, const double* __restrict__ mu,
         const double* __restrict__ log_v, const double* __restrict__ ls, const double* __restrict__ os,
         const double* __restrict__ noise, double c, double* __restrict__ d_log_v, double* __restrict__ ws, int32_t* info) {
-    constexpr int TP8 = 8 * NT8, NL = 32 * NW, ROWS = rows3<NT8, LD>(), TRI = ROWS * (ROWS + 1) / 2, ASZ = ROWS * LD,
-                  KIT = UNR ? (TRI + NL - 1) / NL : 1;
+    constexpr int TP8 = 8 * NT8, NL = 32 * NW, ROWS = rows3<NT8, LD>(), TRI = ROWS * (ROWS + 1) / 2, ASZ = ROWS * LD;
     extern __shared__ double sm[];
     __shared__ PrepTab pt;
     __shared__ unsigned short ijt[TRI];
@@ -403,58 +361,30 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
             sF += lv;
             mw[t] = mu[(size_t)(r0 + t) * L + l];
         }
-        int ij[KIT];      // (i | j << 8) of this lane's entries (UNR only)
-#pragma unroll
-        for (int k = 0; k < KIT; ++k) {
-            const int e = gl + k * NL;
-            ij[k] = e < ntri ? (int)ijt[e < TRI ? e : 0] : -1;
-        }
         gsync<NW>(bar);
-        if constexpr (UNR) {
-            // ---- B_p = K1 + noise I (lower triangle evaluated, mirrored) ; A2 <- 0 -----------------------------------------------
-            {
-                double kv[KIT];
-    #pragma unroll
-                for (int k = 0; k < KIT; ++k) kv[k] = 0.0;
-                for (int cc = sp.n0; cc < nc; ++cc) {
-                    const double o = pt.osc[cc];
-                    eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double) { kv[k] += o * f; });
-                }
-    #pragma unroll
-                for (int k = 0; k < KIT; ++k) {
-                    if (ij[k] >= 0) {
-                        const int i = ij[k] & 255, j = ij[k] >> 8;
-                        const double v = kv[k] + (i == j ? pt.noise : 0.0);
-                        A1[i * LD + j] = v;
-                        A1[j * LD + i] = v;
-                    }
-                }
-            }
-        } else {
-            // ---- B_p = K1 + noise I: every lane accumulates ITS lower-triangle entries in place over the components, then mirrors ----
-            for (int cc = sp.n0; cc < nc; ++cc) {
-                const double o = pt.osc[cc];
-                const bool first = cc == sp.n0;
-                eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double) {
-                    A1[i * LD + j] = (first ? 0.0 : A1[i * LD + j]) + o * f;
-                });
-            }
-    #pragma unroll 1
-            for (int e = gl; e < ntri; e += NL) {
-                const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
-                const double v = A1[i * LD + j] + (i == j ? pt.noise : 0.0);
-                A1[i * LD + j] = v;
-                A1[j * LD + i] = v;
-            }
+        // ---- B_p = K1 + noise I: every lane accumulates ITS lower-triangle entries in place over the components, then mirrors ----
+        for (int cc = sp.n0; cc < nc; ++cc) {
+            const double o = pt.osc[cc];
+            const bool first = cc == sp.n0;
+            eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double) {
+                A1[i * LD + j] = (first ? 0.0 : A1[i * LD + j]) + o * f;
+            });
+        }
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += NL) {
+            const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
+            const double v = A1[i * LD + j] + (i == j ? pt.noise : 0.0);
+            A1[i * LD + j] = v;
+            A1[j * LD + i] = v;
         }
         for (int e = gl; e < ASZ; e += NL) A2[e] = 0.0;
         gsync<NW>(bar);
         {
-            const int bad = grp_cholesky<NT8, LD, NW>(A1, T, dinv, lane, wg, bar);
+            const int bad = grp_cholesky<NT8, LD, NW, TU>(A1, T, dinv, lane, wg, bar);
             if (bad && wg == 0 && lane == 0) atomicCAS(info + 2, 0, l * P_b + p + 1);
         }
         for (int t = gl; t < T; t += NL) sC -= 2.0 * log(dinv[t]);                                            // 192
-        grp_tri_inverse<NT8, LD, NW>(A1, A2, T, dinv, tile, lane, wg, bar);
+        grp_tri_inverse<NT8, LD, NW, TU>(A1, A2, T, dinv, tile, lane, wg, bar);
         if (w.v2) {   // rows of L^-1 for the subject pass: [row][k'], k' = column inside the subject, zero padded to TP
             double* gl_ = ws + w.Lrows + ((size_t)l * N_b + r0) * w.TP;
             int i = 0, k = gl;
@@ -465,75 +395,36 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
                 while (k >= w.TP) { k -= w.TP; ++i; }
             }
         }
-        grp_mm<true, true, NT8, LD, NW>(A2, A2, A3, T, nt8, nk4, g, q, wg);                                     // B^-1 = L^-T L^-1
+        grp_mm<true, true, NT8, LD, NW, TU>(A2, A2, A3, T, nt8, nk4, g, q, wg);                                     // B^-1 = L^-T L^-1
         gsync<NW>(bar);
-        if constexpr (UNR) {
-            // ---- K0_p (+ diag v) into A1 ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta ---------------------------------------
-            {
-                double kv[KIT], bi[KIT];
-    #pragma unroll
-                for (int k = 0; k < KIT; ++k) {
-                    kv[k] = 0.0;
-                    bi[k] = 0.0;
-                    if (ij[k] >= 0) {
-                        const int i = ij[k] & 255, j = ij[k] >> 8;
-                        bi[k] = A3[i * LD + j] * (i == j ? 1.0 : 2.0);
-                    }
-                }
-                for (int cc = 0; cc < sp.n0; ++cc) {
-                    const double o = pt.osc[cc];
-                    double s1 = 0.0, s2 = 0.0;
-                    eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double d2) {
-                        kv[k] += o * f;
-                        const double w_ = bi[k] * f;
-                        s1 += w_;
-                        s2 += w_ * d2;
-                    });
-                    s1 = warp_sum(s1);
-                    s2 = warp_sum(s2);
-                    if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
-                }
-    #pragma unroll
-                for (int k = 0; k < KIT; ++k) {
-                    if (ij[k] >= 0) {
-                        const int i = ij[k] & 255, j = ij[k] >> 8;
-                        sD1 += bi[k] * kv[k];
-                        const double v = kv[k] + (i == j ? ev[i] : 0.0);
-                        A1[i * LD + j] = v;
-                        A1[j * LD + i] = v;
-                    }
-                }
-            }
-        } else {
-            // ---- K0_p (+ diag v) into A1 (accumulated in place over the components) ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta
-            for (int cc = 0; cc < sp.n0; ++cc) {
-                const double o = pt.osc[cc];
-                const bool first = cc == 0;
-                double s1 = 0.0, s2 = 0.0;
-                eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double d2) {
-                    A1[i * LD + j] = (first ? 0.0 : A1[i * LD + j]) + o * f;
-                    const double w_ = A3[i * LD + j] * (i == j ? 1.0 : 2.0) * f;
-                    s1 += w_;
-                    s2 += w_ * d2;
-                });
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
-            }
-    #pragma unroll 1
-            for (int e = gl; e < ntri; e += NL) {
-                const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
-                const double k0 = A1[i * LD + j];
-                sD1 += A3[i * LD + j] * (i == j ? 1.0 : 2.0) * k0;
-                const double v = k0 + (i == j ? ev[i] : 0.0);
-                A1[i * LD + j] = v;
-                A1[j * LD + i] = v;
-            }
+        // ---- K0_p (+ diag v) into A1 (accumulated in place over the components) ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta
+        for (int cc = 0; cc < sp.n0; ++cc) {
+            const double o = pt.osc[cc];
+            const bool first = cc == 0;
+            double s1 = 0.0, s2 = 0.0;
+            eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double d2) {
+                A1[i * LD + j] = (first ? 0.0 : A1[i * LD + j]) + o * f;
+                const double w_ = A3[i * LD + j] * (i == j ? 1.0 : 2.0) * f;
+                s1 += w_;
+                s2 += w_ * d2;
+            });
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
+        }
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += NL) {
+            const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
+            const double k0 = A1[i * LD + j];
+            sD1 += A3[i * LD + j] * (i == j ? 1.0 : 2.0) * k0;
+            const double v = k0 + (i == j ? ev[i] : 0.0);
+            A1[i * LD + j] = v;
+            A1[j * LD + i] = v;
         }
         gsync<NW>(bar);
-        grp_mm<false, false, NT8, LD, NW>(A1, A3, A2, T, nt8, nk4, g, q, wg);                                   // X1 = (diag v + K0) B^-1
+        grp_mm<false, false, NT8, LD, NW, TU>(A1, A3, A2, T, nt8, nk4, g, q, wg);                                   // X1 = (diag v + K0) B^-1
         gsync<NW>(bar);
-        grp_mm<false, false, NT8, LD, NW>(A3, A2, A1, T, nt8, nk4, g, q, wg);                                   // X2 = B^-1 X1
+        grp_mm<false, false, NT8, LD, NW, TU>(A3, A2, A1, T, nt8, nk4, g, q, wg);                                   // X2 = B^-1 X1
         gsync<NW>(bar);
         if (w.v2) {
             double* gb = ws + w.bmu + (size_t)l * N_b + r0;
@@ -552,69 +443,34 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
                 while (j >= T) { j -= T; ++i; }
             }
         }
-        if constexpr (UNR) {
-            // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] against d K1 / d theta ; noise ; Bt ; d_log_v -----------------------
-            {
-                double gB[KIT];
-    #pragma unroll
-                for (int k = 0; k < KIT; ++k) {
-                    gB[k] = 0.0;
-                    if (ij[k] >= 0) {
-                        const int i = ij[k] & 255, j = ij[k] >> 8;
-                        const double b_ = A3[i * LD + j];
-                        if (i == j) {
-                            gB[k] = b_ - A1[i * LD + i];
-                            gno += gB[k];
-                            const double bt = b_ * ev[i];
-                            sBt += bt;
-                            d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
-                        } else {
-                            gB[k] = 2.0 * b_ - (A1[i * LD + j] + A1[j * LD + i]);
-                        }
-                    }
-                }
-                for (int cc = sp.n0; cc < nc; ++cc) {
-                    double s1 = 0.0, s2 = 0.0;
-                    eval_entries<KIT, LD>(pt, cc, XC, ij, [&](int k, double f, double d2) {
-                        const double w_ = gB[k] * f;
-                        s1 += w_;
-                        s2 += w_ * d2;
-                    });
-                    s1 = warp_sum(s1);
-                    s2 = warp_sum(s2);
-                    if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
-                }
-            }
+        // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] -> A2 (X1 is dead), then against d K1 / d theta ; noise ; Bt ; d_log_v
+#pragma unroll 1
+        for (int e = gl; e < ntri; e += NL) {
+            const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
+            const double b_ = A3[i * LD + j];
+            double gB;
+            if (i == j) {
+                gB = b_ - A1[i * LD + i];
+                gno += gB;
+                const double bt = b_ * ev[i];
+                sBt += bt;
+                d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
             } else {
-            // ---- local adjoint of B_p: (B^-1 - X2) [times c at the end] -> A2 (X1 is dead), then against d K1 / d theta ; noise ; Bt ; d_log_v
-    #pragma unroll 1
-            for (int e = gl; e < ntri; e += NL) {
-                const int v_ = ijt[e], i = v_ & 255, j = v_ >> 8;
-                const double b_ = A3[i * LD + j];
-                double gB;
-                if (i == j) {
-                    gB = b_ - A1[i * LD + i];
-                    gno += gB;
-                    const double bt = b_ * ev[i];
-                    sBt += bt;
-                    d_log_v[(size_t)(r0 + i) * L + l] = c * (bt - 1.0);
-                } else {
-                    gB = 2.0 * b_ - (A1[i * LD + j] + A1[j * LD + i]);
-                }
-                A2[i * LD + j] = gB;
+                gB = 2.0 * b_ - (A1[i * LD + j] + A1[j * LD + i]);
             }
-            for (int cc = sp.n0; cc < nc; ++cc) {
-                double s1 = 0.0, s2 = 0.0;
-                eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double d2) {
-                    const double w_ = A2[i * LD + j] * f;
-                    s1 += w_;
-                    s2 += w_ * d2;
-                });
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
-            }
-            }
+            A2[i * LD + j] = gB;
+        }
+        for (int cc = sp.n0; cc < nc; ++cc) {
+            double s1 = 0.0, s2 = 0.0;
+            eval_tri<LD>(pt, cc, XC, ijt, gl, NL, ntri, [&](int i, int j, double f, double d2) {
+                const double w_ = A2[i * LD + j] * f;
+                s1 += w_;
+                s2 += w_ * d2;
+            });
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) { hacc[cc] += s1; hacc[NCM + cc] += s2; }
+        }
     }
     // ---- one partial row per warp (summed in fixed order by the reduce kernel) ------------------------------------------------
     __syncwarp();
@@ -647,19 +503,19 @@ int groups_per_cta3(int nslots) {
     return n < 1 ? 1 : n;
 }
 
-template <int NT8, int LD, int NW, bool UNR>
+template <int NT8, int LD, int NW, bool TU>
 int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int nslots = slots_of(sp);
     const int gpc = groups_per_cta3<NT8, LD, NW>(nslots), pw = gpc * NW;
     const size_t smem = sizeof(double) * (size_t)gpc * group_doubles3<NT8, LD, NW>(nslots);
     static size_t attr = 0;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_prep3<NT8, LD, NW, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_prep3<NT8, LD, NW, TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return lvae_cuda_rc(e);
         attr = smem;
     }
     if (w.nprep % pw != 0) return LVAE_E_BADARG;
-    k_prep3<NT8, LD, NW, UNR><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, nslots, p->x, p->offsets,
+    k_prep3<NT8, LD, NW, TU><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, nslots, p->x, p->offsets,
                                                                           p->mu, p->log_v, p->lengthscale, p->outputscale,
                                                                           p->noise, 0.5 * p->scale, p->d_log_v, p->workspace,
                                                                           p->info);
@@ -673,8 +529,8 @@ int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
 bool lvae_prep3_supported(const lvae_kld_problem_t* p, const KldLayout& w) {
     (void)w;
     {
-        const char* e = getenv("LVAE_PREP3_LONG");       // measurement switch: also take 24 < T <= 40 (4 warps per task)
-        if (e && e[0] == '1') return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 40 && p->T_max >= 1;
+        const char* e = getenv("LVAE_PREP3_LONG");       // "0": leave 24 < T <= 40 to k_prep_warp<4> (A/B measurements)
+        if (!(e && e[0] == '0')) return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 40 && p->T_max >= 1;
     }
     // T <= 24 (one warp per task).  For 24 < T <= 40 the 4-warps-per-task instantiation of this kernel measured slower than
     // k_prep_warp<4> of lvae_prep.cu (7.8 vs 4.7 ms at cfg4), so that range stays with the older kernel.
@@ -699,8 +555,7 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
 
 int lvae_prep3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int T = p->T_max;
-    const bool uniform = p->sum_T2 == (int64_t)p->P_b * T * T;      // every subject has exactly T_max rows
-    if (T <= 20) return uniform ? launch3<3, 20, 1, true>(p, sp, w, st) : launch3<3, 20, 1, false>(p, sp, w, st);
-    if (T <= 24) return uniform ? launch3<3, 28, 1, true>(p, sp, w, st) : launch3<3, 28, 1, false>(p, sp, w, st);
+    if (T <= 20) return launch3<3, 20, 1, true>(p, sp, w, st);
+    if (T <= 24) return launch3<3, 28, 1, true>(p, sp, w, st);
     return launch3<5, 44, 4, false>(p, sp, w, st);
 }
