@@ -295,6 +295,7 @@ def main():
     const = L * (N_b * world) / 2 if ragged else L * P_tot * int(b.T) / 2
     call = (ops.make_kld_call(st, L, M, Q, Tl, device, natural_gradient=True, path=args.path) if ragged else
             ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path))
+    is_split = isinstance(call, ops.SplitKldCall)
     ng_ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=torch.float64, device=device)
     ng_info = torch.zeros(4, dtype=torch.int32, device=device)
     lr = 1e-3
@@ -328,7 +329,7 @@ def main():
     elif M <= 64:
         kernel_path = ("fused (one DMMA kernel per subject pass)" if T_max <= 24 or args.path == 2 else
                        "split: subjects with T <= 24 fused v2 + prep v3, longer ones fused v1 + 4-warp prep" if
-                       isinstance(call, ops.SplitKldCall) else "fused v1")
+                       is_split else "fused v1")
     else:
         kernel_path = "gemm (U/V materialised, S = U^T U and Y = V W as batched DMMA GEMMs)" if T_max <= 24 else "generic"
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)   # > 126 MB L2
@@ -374,6 +375,8 @@ def main():
     finite = bool(torch.isfinite(call.kld_per_latent).all() and torch.isfinite(H).all())
 
     # ---- end to end through the public API with host buffers --------------------------------------------------
+    del call                                   # its workspace (tens of GB at M > 64 with large minibatches) is not needed any more
+    torch.cuda.empty_cache()
     m.copy_(m0); H.copy_(H0)
     hx, hmu, hlv = b.x.pin_memory(), b.mu.pin_memory(), b.log_v.pin_memory()
     out_mu = torch.empty_like(b.mu).pin_memory()
