@@ -21,6 +21,9 @@ constexpr int NMT = RG / 8;
 constexpr int LDL = 28;
 constexpr int GT = LVAE_F2_GT;
 constexpr int NCB = 8;             // components handled by the register accumulators
+#ifndef LVAE_ADJ_CTAS
+#define LVAE_ADJ_CTAS 3
+#endif
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -78,98 +81,86 @@ __device__ __forceinline__ void gather_cov(const CompTab& ct, int c_begin, int c
         dst[((size_t)(c - c_begin) * CS + sl) * ld + r] = (dim >= 0 && r < nvalid) ? src[(size_t)r * Q + dim] : 0.0;
     }
 }
-// Un-scaled values of ONE component on this lane's entries of a row group: rows 8*mt + g (mt < nmt), column pairs
-// (j0, j0 + 1), j0 = colw + 8*nt + 2q (nt < NTW).  NM (number of categorical / binary factors) and RBF are compile-time,
-// so the body is straight-line: per factor one FMA + compare per column (cat: a - b == 0, bin: a + b == 2, both written
-// as fma(sgn, b, a) == tgt, exactly rounded like the reference's subtraction / addition), per SE factor one exp per column.
-// `fn(mt, nt, f0, f1, d20, d21)` consumes the values.  Row / column validity is the caller's business.
+// Un-scaled values of ONE component on this lane's entries of ONE 8-row tile of a row group: row t = 8*mt + g, column pairs
+// (j0, j0 + 1), j0 = colw + 8*nt + 2q (nt < NTW).  NM (number of categorical / binary factors) and RBF are compile-time, so
+// the body is straight-line: per factor one FMA + compare per column (cat: a - b == 0, bin: a + b == 2, both written as
+// fma(sgn, b, a) == tgt, exactly rounded like the reference's subtraction / addition), per SE factor one exp per column.
+// `fn(nt, f0, f1, d20, d21)` consumes the values.  Row / column validity is the caller's business.  The callers keep the loop
+// over the row tiles ROLLED: a third of the code and of the live registers of the fully unrolled form.
 template <int NM, bool RBF, int NTW, class Fn>
-__device__ __forceinline__ void eval_block(const CompTab& ct, int c, const double* __restrict__ XCc, const double* __restrict__ ZCc,
-                                           int ldz, int nmt, int g, int q, int colw, Fn&& fn) {
-    double sgn[NM > 0 ? NM : 1], tgt[NM > 0 ? NM : 1];
+__device__ __forceinline__ void eval_row_block(const CompTab& ct, int c, const double* __restrict__ XCc,
+                                               const double* __restrict__ ZCc, int ldz, int t, int q, int colw, Fn&& fn) {
+    double sgn[NM > 0 ? NM : 1], tgt[NM > 0 ? NM : 1], am[NM > 0 ? NM : 1];
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         const bool cat = ct.mtype[c][i] == LVAE_CAT;
         sgn[i] = cat ? -1.0 : 1.0;
         tgt[i] = cat ? 0.0 : 2.0;
+        am[i] = XCc[(1 + i) * RG + t];
     }
     const double h = ct.negh[c];
+    const double ar = RBF ? XCc[t] : 0.0;
 #pragma unroll
-    for (int mt = 0; mt < NMT; ++mt) {
-        if (mt < nmt) {
-            const int t = 8 * mt + g;
-            double am[NM > 0 ? NM : 1];
+    for (int nt = 0; nt < NTW; ++nt) {
+        const int j0 = colw + 8 * nt + 2 * q;
+        bool on0 = true, on1 = true;
 #pragma unroll
-            for (int i = 0; i < NM; ++i) am[i] = XCc[(1 + i) * RG + t];
-            const double ar = RBF ? XCc[t] : 0.0;
-#pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                const int j0 = colw + 8 * nt + 2 * q;
-                bool on0 = true, on1 = true;
-#pragma unroll
-                for (int i = 0; i < NM; ++i) {
-                    const double2 b = *reinterpret_cast<const double2*>(ZCc + (1 + i) * ldz + j0);
-                    on0 = on0 && (fma(sgn[i], b.x, am[i]) == tgt[i]);
-                    on1 = on1 && (fma(sgn[i], b.y, am[i]) == tgt[i]);
-                }
-                double e0 = 1.0, e1 = 1.0, d20 = 0.0, d21 = 0.0;
-                if (RBF) {
-                    const double2 b = *reinterpret_cast<const double2*>(ZCc + j0);
-                    const double t0 = ar - b.x, t1 = ar - b.y;
-                    d20 = t0 * t0; d21 = t1 * t1;
-                    e0 = exp_neg(d20 * h, ct.etab);
-                    e1 = exp_neg(d21 * h, ct.etab);
-                }
-                fn(mt, nt, on0 ? e0 : 0.0, on1 ? e1 : 0.0, d20, d21);
-            }
+        for (int i = 0; i < NM; ++i) {
+            const double2 b = *reinterpret_cast<const double2*>(ZCc + (1 + i) * ldz + j0);
+            on0 = on0 && (fma(sgn[i], b.x, am[i]) == tgt[i]);
+            on1 = on1 && (fma(sgn[i], b.y, am[i]) == tgt[i]);
         }
+        double e0 = 1.0, e1 = 1.0, d20 = 0.0, d21 = 0.0;
+        if (RBF) {
+            const double2 b = *reinterpret_cast<const double2*>(ZCc + j0);
+            const double t0 = ar - b.x, t1 = ar - b.y;
+            d20 = t0 * t0; d21 = t1 * t1;
+            e0 = exp_neg(d20 * h, ct.etab);
+            e1 = exp_neg(d21 * h, ct.etab);
+        }
+        fn(nt, on0 ? e0 : 0.0, on1 ? e1 : 0.0, d20, d21);
     }
 }
 // generic shape (2-3 factors): run-time factor loop
 template <int NTW, class Fn>
-__device__ __forceinline__ void eval_generic(const CompTab& ct, int c, const double* __restrict__ XCc, const double* __restrict__ ZCc,
-                                          int ldz, int nmt, int g, int q, int colw, Fn& fn) {
+__device__ __forceinline__ void eval_row_generic(const CompTab& ct, int c, const double* __restrict__ XCc,
+                                                 const double* __restrict__ ZCc, int ldz, int t, int q, int colw, Fn& fn) {
     const int nm = ct.nmask[c];
     const double h = ct.negh[c];
     const bool rbf = ct.rbf[c] != 0;
 #pragma unroll
-    for (int mt = 0; mt < NMT; ++mt) {
-        if (mt >= nmt) continue;
-        const int t = 8 * mt + g;
-#pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) {
-            const int j0 = colw + 8 * nt + 2 * q;
-            bool on0 = true, on1 = true;
-            for (int i = 0; i < nm; ++i) {
-                const double a = XCc[(1 + i) * RG + t];
-                const double2 b = *reinterpret_cast<const double2*>(ZCc + (1 + i) * ldz + j0);
-                if (ct.mtype[c][i] == LVAE_CAT) { on0 = on0 && (a - b.x == 0.0); on1 = on1 && (a - b.y == 0.0); }
-                else { on0 = on0 && (a + b.x == 2.0); on1 = on1 && (a + b.y == 2.0); }
-            }
-            double e0 = 1.0, e1 = 1.0, d20 = 0.0, d21 = 0.0;
-            if (rbf) {
-                const double a = XCc[t];
-                const double2 b = *reinterpret_cast<const double2*>(ZCc + j0);
-                const double t0 = a - b.x, t1 = a - b.y;
-                d20 = t0 * t0; d21 = t1 * t1;
-                e0 = exp_neg(d20 * h, ct.etab);
-                e1 = exp_neg(d21 * h, ct.etab);
-            }
-            fn(mt, nt, on0 ? e0 : 0.0, on1 ? e1 : 0.0, d20, d21);
+    for (int nt = 0; nt < NTW; ++nt) {
+        const int j0 = colw + 8 * nt + 2 * q;
+        bool on0 = true, on1 = true;
+        for (int i = 0; i < nm; ++i) {
+            const double a = XCc[(1 + i) * RG + t];
+            const double2 b = *reinterpret_cast<const double2*>(ZCc + (1 + i) * ldz + j0);
+            if (ct.mtype[c][i] == LVAE_CAT) { on0 = on0 && (a - b.x == 0.0); on1 = on1 && (a - b.y == 0.0); }
+            else { on0 = on0 && (a + b.x == 2.0); on1 = on1 && (a + b.y == 2.0); }
         }
+        double e0 = 1.0, e1 = 1.0, d20 = 0.0, d21 = 0.0;
+        if (rbf) {
+            const double a = XCc[t];
+            const double2 b = *reinterpret_cast<const double2*>(ZCc + j0);
+            const double t0 = a - b.x, t1 = a - b.y;
+            d20 = t0 * t0; d21 = t1 * t1;
+            e0 = exp_neg(d20 * h, ct.etab);
+            e1 = exp_neg(d21 * h, ct.etab);
+        }
+        fn(nt, on0 ? e0 : 0.0, on1 ? e1 : 0.0, d20, d21);
     }
 }
 // warp-uniform dispatch on the component's shape: straight-line code for the shapes kernel_gen.py produces without
 // missing-value masks (SE, cat/bin x SE, cat/bin), a run-time factor loop for 2-3 factors
 template <int NTW, class Fn>
-__device__ __forceinline__ void eval_component(const CompTab& ct, int c, const double* __restrict__ XCc,
-                                               const double* __restrict__ ZCc, int ldz, int nmt, int g, int q, int colw, Fn&& fn) {
+__device__ __forceinline__ void eval_row(const CompTab& ct, int c, const double* __restrict__ XCc, const double* __restrict__ ZCc,
+                                         int ldz, int t, int q, int colw, Fn&& fn) {
     const int nm = ct.nmask[c];
     const bool rbf = ct.rbf[c] != 0;
-    if (nm == 0) eval_block<0, true, NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
-    else if (nm == 1 && rbf) eval_block<1, true, NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
-    else if (nm == 1) eval_block<1, false, NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
-    else eval_generic<NTW>(ct, c, XCc, ZCc, ldz, nmt, g, q, colw, fn);
+    if (nm == 0) eval_row_block<0, true, NTW>(ct, c, XCc, ZCc, ldz, t, q, colw, fn);
+    else if (nm == 1 && rbf) eval_row_block<1, true, NTW>(ct, c, XCc, ZCc, ldz, t, q, colw, fn);
+    else if (nm == 1) eval_row_block<1, false, NTW>(ct, c, XCc, ZCc, ldz, t, q, colw, fn);
+    else eval_row_generic<NTW>(ct, c, XCc, ZCc, ldz, t, q, colw, fn);
 }
 // single entry, both sides from the gathered row covariates (K1 components on (X_p, X_p))
 __device__ __forceinline__ double eval_rows(const CompTab& ct, int c, const double* __restrict__ XCc, int ldx, int t, int t2,
@@ -256,36 +247,34 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
             const int t = e / RG, k = e - t * RG, lo = blo[t];
             Lg[t * LDL + k] = (k >= lo && k < bhi[t]) ? Lrows[(size_t)(row0 + t) * w.TP + (k - lo)] : 0.0;
         }
-        // ---- Kxz from the gathered covariates (own columns) ; partial dots of r = Kxz a - mu ---------------------------------
-        {
-            double kx[NMT][NTW][2];
+        // ---- Kxz from the gathered covariates (own columns), one 8-row tile at a time ; partial dots of r = Kxz a - mu -----
+#pragma unroll 1
+        for (int mt = 0; mt < NMT; ++mt) {
+            const int t = 8 * mt + g;
+            double kx[NTW][2];
 #pragma unroll
-            for (int mt = 0; mt < NMT; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) kx[mt][nt][0] = kx[mt][nt][1] = 0.0;
-            for (int cc = 0; cc < sp.n0; ++cc) {
-                const double o = ct.osc[cc];
-                eval_component<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, nmt, g, q, colw,
-                                    [&](int mt, int nt, double f0, double f1, double, double) {
-                                        kx[mt][nt][0] += o * f0;
-                                        kx[mt][nt][1] += o * f1;
-                                    });
-            }
-#pragma unroll
-            for (int mt = 0; mt < NMT; ++mt) {
-                const int t = 8 * mt + g;
-                double pr = 0.0;
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) {
-                    const int j0 = colw + 8 * nt + 2 * q;
-                    const double k0_ = (t < R && j0 < M) ? kx[mt][nt][0] : 0.0, k1_ = (t < R && j0 + 1 < M) ? kx[mt][nt][1] : 0.0;
-                    *reinterpret_cast<double2*>(K + t * LDM + j0) = make_double2(k0_, k1_);
-                    pr += k0_ * av[j0] + k1_ * av[j0 + 1];
+            for (int nt = 0; nt < NTW; ++nt) kx[nt][0] = kx[nt][1] = 0.0;
+            if (mt < nmt) {
+                for (int cc = 0; cc < sp.n0; ++cc) {
+                    const double o = ct.osc[cc];
+                    eval_row<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, t, q, colw,
+                                  [&](int nt, double f0, double f1, double, double) {
+                                      kx[nt][0] += o * f0;
+                                      kx[nt][1] += o * f1;
+                                  });
                 }
-                pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-                pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-                if (q == 0) rpart[wl * RG + t] = pr;
             }
+            double pr = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                const int j0 = colw + 8 * nt + 2 * q;
+                const double k0_ = (t < R && j0 < M) ? kx[nt][0] : 0.0, k1_ = (t < R && j0 + 1 < M) ? kx[nt][1] : 0.0;
+                *reinterpret_cast<double2*>(K + t * LDM + j0) = make_double2(k0_, k1_);
+                pr += k0_ * av[j0] + k1_ * av[j0 + 1];
+            }
+            pr += __shfl_xor_sync(0xffffffffu, pr, 1);
+            pr += __shfl_xor_sync(0xffffffffu, pr, 2);
+            if (q == 0) rpart[wl * RG + t] = pr;
         }
         __syncthreads();
         if (tid < RG) {
@@ -382,7 +371,7 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
 }
 
 template <int NTW>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, LVAE_ADJ_CTAS)
 k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b,
       const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls, const double* __restrict__ os,
       double c, double* __restrict__ ws) {
@@ -430,35 +419,35 @@ k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, i
         }
         gather_cov(ct, 0, nc, x + (size_t)row0 * Q, Q, RG, R, RG, XC);
         __syncthreads();
-        // ---- adjoint of Kxz = 2c u a^T + 2Y (own columns, registers) against d k_c / d theta of the K0 components ----------------------
-        double gb[NMT][NTW][2];
-#pragma unroll
-        for (int mt = 0; mt < NMT; ++mt) {
+        // ---- adjoint of Kxz = 2c u a^T + 2Y (own columns) against d k_c / d theta of the K0 components, one 8-row tile at a time ---
+#pragma unroll 1
+        for (int mt = 0; mt < nmt; ++mt) {
             const int t = 8 * mt + g;
-            const bool rv = mt < nmt && t < R;
+            const bool rv = t < R;
             const double ut = 2.0 * c * us[t];
+            double gb[NTW][2];
 #pragma unroll
             for (int nt = 0; nt < NTW; ++nt) {
                 const int j0 = colw + 8 * nt + 2 * q;
                 double2 y = make_double2(0.0, 0.0);
                 if (rv) y = *reinterpret_cast<const double2*>(Yg + (size_t)(row0 + t) * MP + j0);
-                gb[mt][nt][0] = (rv && j0 < M) ? ut * av[j0] + 2.0 * y.x : 0.0;
-                gb[mt][nt][1] = (rv && j0 + 1 < M) ? ut * av[j0 + 1] + 2.0 * y.y : 0.0;
+                gb[nt][0] = (rv && j0 < M) ? ut * av[j0] + 2.0 * y.x : 0.0;
+                gb[nt][1] = (rv && j0 + 1 < M) ? ut * av[j0 + 1] + 2.0 * y.y : 0.0;
             }
-        }
-        for (int cc = 0; cc < sp.n0; ++cc) {
-            double s1 = 0.0, s2 = 0.0;
-            eval_component<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, nmt, g, q, colw,
-                                [&](int mt, int nt, double f0, double f1, double d20, double d21) {
-                                    const double w0 = gb[mt][nt][0] * f0, w1 = gb[mt][nt][1] * f1;
-                                    s1 += w0 + w1;
-                                    s2 += w0 * d20 + w1 * d21;
-                                });
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            if (lane == 0) {
-                hypacc[wl][sp.n_ls + cc] += s1;
-                if (ct.rbf[cc]) hypacc[wl][ct.lsidx[cc]] += s2 * ct.lsw[cc];
+            for (int cc = 0; cc < sp.n0; ++cc) {
+                double s1 = 0.0, s2 = 0.0;
+                eval_row<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, t, q, colw,
+                              [&](int nt, double f0, double f1, double d20, double d21) {
+                                  const double w0 = gb[nt][0] * f0, w1 = gb[nt][1] * f1;
+                                  s1 += w0 + w1;
+                                  s2 += w0 * d20 + w1 * d21;
+                              });
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) {
+                    hypacc[wl][sp.n_ls + cc] += s1;
+                    if (ct.rbf[cc]) hypacc[wl][ct.lsidx[cc]] += s2 * ct.lsw[cc];
+                }
             }
         }
         // ---- Q = Y V^T over this warp's k-slice, subject-diagonal upper tiles ; adjoint of B_p = -(c u u^T + Q) ---------------------
