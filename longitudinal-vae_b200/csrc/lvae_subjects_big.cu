@@ -419,35 +419,33 @@ k_adj(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, i
         }
         gather_cov(ct, 0, nc, x + (size_t)row0 * Q, Q, RG, R, RG, XC);
         __syncthreads();
-        // ---- adjoint of Kxz = 2c u a^T + 2Y (own columns) against d k_c / d theta of the K0 components, one 8-row tile at a time ---
+        // ---- adjoint of Kxz = 2c u a^T + 2Y (own columns) against d k_c / d theta of the K0 components: component loop outside,
+        // rolled row-tile loop inside (Y re-read per component, from L1), so each component needs ONE warp reduction per group
+        for (int cc = 0; cc < sp.n0; ++cc) {
+            const double* XCc = XC + cc * CS * RG;
+            const double* ZCc = ZC + cc * CS * MP;
+            double s1 = 0.0, s2 = 0.0;
 #pragma unroll 1
-        for (int mt = 0; mt < nmt; ++mt) {
-            const int t = 8 * mt + g;
-            const bool rv = t < R;
-            const double ut = 2.0 * c * us[t];
-            double gb[NTW][2];
-#pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                const int j0 = colw + 8 * nt + 2 * q;
-                double2 y = make_double2(0.0, 0.0);
-                if (rv) y = *reinterpret_cast<const double2*>(Yg + (size_t)(row0 + t) * MP + j0);
-                gb[nt][0] = (rv && j0 < M) ? ut * av[j0] + 2.0 * y.x : 0.0;
-                gb[nt][1] = (rv && j0 + 1 < M) ? ut * av[j0 + 1] + 2.0 * y.y : 0.0;
-            }
-            for (int cc = 0; cc < sp.n0; ++cc) {
-                double s1 = 0.0, s2 = 0.0;
-                eval_row<NTW>(ct, cc, XC + cc * CS * RG, ZC + cc * CS * MP, MP, t, q, colw,
-                              [&](int nt, double f0, double f1, double d20, double d21) {
-                                  const double w0 = gb[nt][0] * f0, w1 = gb[nt][1] * f1;
-                                  s1 += w0 + w1;
-                                  s2 += w0 * d20 + w1 * d21;
-                              });
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                if (lane == 0) {
-                    hypacc[wl][sp.n_ls + cc] += s1;
-                    if (ct.rbf[cc]) hypacc[wl][ct.lsidx[cc]] += s2 * ct.lsw[cc];
+            for (int mt = 0; mt < nmt; ++mt) {
+                const int t = 8 * mt + g;
+                if (t < R) {
+                    const double ut = 2.0 * c * us[t];
+                    const double* yrow = Yg + (size_t)(row0 + t) * MP;
+                    eval_row<NTW>(ct, cc, XCc, ZCc, MP, t, q, colw, [&](int nt, double f0, double f1, double d20, double d21) {
+                        const int j0 = colw + 8 * nt + 2 * q;
+                        const double2 y = *reinterpret_cast<const double2*>(yrow + j0);
+                        const double w0 = j0 < M ? (ut * av[j0] + 2.0 * y.x) * f0 : 0.0;
+                        const double w1 = j0 + 1 < M ? (ut * av[j0 + 1] + 2.0 * y.y) * f1 : 0.0;
+                        s1 += w0 + w1;
+                        s2 += w0 * d20 + w1 * d21;
+                    });
                 }
+            }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) {
+                hypacc[wl][sp.n_ls + cc] += s1;
+                if (ct.rbf[cc]) hypacc[wl][ct.lsidx[cc]] += s2 * ct.lsw[cc];
             }
         }
         // ---- Q = Y V^T over this warp's k-slice, subject-diagonal upper tiles ; adjoint of B_p = -(c u u^T + Q) ---------------------
