@@ -290,3 +290,57 @@ def test_device_exp_accuracy():
     big = ref > 1e-300
     assert np.abs(got[big] - ref[big]).max() / 1.0 >= 0 and (np.abs(got[big] - ref[big]) / ref[big]).max() < 4.5e-16
     assert np.all(got[~big] <= 1e-300) and np.all(got >= 0)
+
+
+def test_cat_kernel_mod_matches_reference_formula():
+    """kernel_spec.CatKernelMod (kernel_spec.py:35-55): 1 on equal ids, -1/(num-1) elsewhere (bit-exact: the mask is exact)."""
+    from lvae_b200.kernel_spec import CatKernelMod
+    x1 = torch.tensor([0.0, 1.0, 2.0, 1.0, 5.0], dtype=torch.float64, device="cuda").reshape(-1, 1)
+    x2 = torch.tensor([1.0, 5.0, 7.0], dtype=torch.float64, device="cuda").reshape(-1, 1)
+    num = 6
+    K = CatKernelMod(num, active_dims=0)(x1, x2).evaluate()
+    m1, m2 = torch.meshgrid(x1.view(-1), x2.view(-1), indexing="ij")
+    ref = (m1 - m2 == 0).double() + (-1 / (num - 1)) * (m1 - m2 != 0).double()
+    assert K.shape == ref.shape and torch.equal(K.reshape(ref.shape), ref)
+
+
+def test_gp_model_modules_drive_the_iter_bound():
+    """The authors' gpytorch-free GP_model.py classes (GP_model.py:7-236; parameters `_log_scale`, `_log_lengthscale`,
+    `_log_noise`) as covar_module0/1 + likelihood of minibatch_KLD_upper_bound_iter: bound, natural gradients, d_mu and the
+    hyper-parameter gradients (chained back to the constrained values) against the reference golden."""
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200 import GP_model as GM
+    g = load_golden("cfg4_ragged")
+    L = g["mu"].shape[1]
+    cm0, cm1 = GM.generate_kernel_batched(L, **g["lists"], id_covariate=2)
+    cm0, cm1 = cm0.double().cuda(), cm1.double().cuda()
+    lik = GM.Likelihoods(L, 1.0).double().cuda()
+    lik.noise = torch.from_numpy(g["noise"]).cuda()
+    i_c = i_l = 0
+    params = []
+    for mod in (cm0, cm1):
+        for sk in mod.kernels:
+            sk.scale = torch.from_numpy(g["outputscale"][i_c]).cuda()
+            params.append((sk._log_scale, sk.min_log_scale))
+            i_c += 1
+            for rb in [mm for mm in sk.modules() if isinstance(mm, GM.RbfKernel)]:
+                rb.lengthscale = torch.from_numpy(g["lengthscale"][i_l]).cuda()
+                params.append((rb._log_lengthscale, rb.min_log_lengthscale))
+                i_l += 1
+    params.append((lik._log_noise, lik.min_log_noise))
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    mu = t("mu").requires_grad_(True)
+    P_b = len(g["offsets"]) - 1
+    kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, t("m"), t("H"), t("x"), mu, t("log_v"), t("z"),
+                                                    int(g["P_tot"]), P_b, int(g["N_tot"]), True, 2, float(g["eps"]))
+    kld.sum().backward()
+    assert abs(kld.item() - float(g["kld"])) <= TOL * abs(float(g["kld"]))
+    assert rel(gm, g["grad_m"]) < TOL and rel(gH, g["grad_H"]) < TOL and rel(mu.grad, g["d_mu"]) < TOL
+    # d/d(constrained value) = d/d(raw) / (value * sigmoid(raw - min_log))
+    got = []
+    for raw, mn in params:
+        val = torch.exp(mn + torch.nn.functional.softplus(raw.detach() - mn))
+        got.append((raw.grad / (val * torch.sigmoid(raw.detach() - mn))).reshape(-1))
+    got = torch.cat(got).cpu().numpy()
+    ref = golden_hyper_vector(g)
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
