@@ -486,6 +486,39 @@ def main():
         b__.record(); torch.cuda.synchronize()
         lat = {"spb": spb2, "ms_per_step": a_.elapsed_time(b__) / 50, "subjects_per_s": spb2 / (a_.elapsed_time(b__) / 50 * 1e-3),
                "what": "spb = 20 (the reference's default minibatch), device-resident inputs, bound + gradients + NG update"}
+        try:      # the same small minibatch through the public API with pinned host inputs (Python + launch overhead regime)
+            hx2, hmu2, hlv2 = b.x[:rows].pin_memory(), b.mu[:rows].pin_memory(), b.log_v[:rows].pin_memory()
+            st2 = {"m": m0.clone(), "H": H0.clone()}
+            o_mu = torch.empty_like(b.mu[:rows]).pin_memory()
+
+            def small_api():
+                xd = hx2.to(device, non_blocking=True)
+                mud = hmu2.to(device, non_blocking=True).requires_grad_(True)
+                lvd = hlv2.to(device, non_blocking=True).requires_grad_(True)
+                if ragged:
+                    kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, st2["m"], st2["H"], xd, mud, lvd, z, P_tot,
+                                                                    spb2, N_b, True, 2, 1e-6)
+                else:
+                    kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, st2["m"], st2["H"], xd, mud, lvd, z, P_tot, spb2,
+                                                               int(b.T), True, 1e-6)
+                kld.sum().backward()
+                st2["m"], st2["H"] = natural_gradient_step(st2["m"], st2["H"], gm, gH, lr)
+                o_mu.copy_(mud.grad, non_blocking=True)
+                cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True)
+            EF.set_error_check("deferred")
+            for _ in range(5):
+                small_api()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(50):
+                small_api()
+            torch.cuda.synchronize()
+            lat["e2e_ms_per_step"] = (time.perf_counter() - t0) / 50 * 1e3
+            lat["e2e_subjects_per_s"] = spb2 / (lat["e2e_ms_per_step"] * 1e-3)
+            EF.check_errors()
+            EF.set_error_check("immediate")
+        except Exception as ex:
+            lat["e2e_unavailable"] = repr(ex)[:160]
         try:      # the same step captured once into a CUDA graph (the C ABI is stream-ordered and capture-safe) and replayed
             side = torch.cuda.Stream(device)
             side.wait_stream(torch.cuda.current_stream(device))

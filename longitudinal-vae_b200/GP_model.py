@@ -12,7 +12,17 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import ops
-from .spec import FlatComponent, build_structure, flatten, latent_count
+from .spec import FlatComponent, Raw, build_structure, flatten, latent_count
+
+
+def _min_float(module, name):
+    """A `min_log_*` buffer as a Python float, read once (no device sync on the hot path)."""
+    key = "_f_" + name
+    v = module.__dict__.get(key)
+    if v is None:
+        v = float(getattr(module, name))
+        module.__dict__[key] = v
+    return v
 
 
 def _bounded(raw, min_log):
@@ -86,7 +96,7 @@ class RbfKernel(_DenseModule):
             self._log_lengthscale.copy_(torch.log(torch.as_tensor(lengthscale) - torch.exp(self.min_log_lengthscale)))
 
     def _flat_components(self):
-        return [FlatComponent(None, [('rbf', self.dim, self.lengthscale.reshape(-1))])]
+        return [FlatComponent(None, [('rbf', self.dim, Raw(self._log_lengthscale, 'bounded', _min_float(self, 'min_log_lengthscale')))])]
 
 
 class ScaleKernel(_DenseModule):
@@ -109,7 +119,7 @@ class ScaleKernel(_DenseModule):
             self._log_scale.copy_(torch.log(torch.as_tensor(scale) - torch.exp(self.min_log_scale)))
 
     def _flat_components(self):
-        s = FlatComponent(self.scale.reshape(-1), [])
+        s = FlatComponent(Raw(self._log_scale, 'bounded', _min_float(self, 'min_log_scale')), [])
         return [s.times(c) for c in flatten(self.kernel)]
 
 

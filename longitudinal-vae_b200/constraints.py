@@ -18,6 +18,14 @@ class GreaterThan(torch.nn.Module):
     def transform(self, raw):
         return F.softplus(raw) + self.lower_bound
 
+    def lower_float(self):
+        """The lower bound as a Python float, read from the buffer once (no device sync on the hot path)."""
+        v = self.__dict__.get("_lower_f")
+        if v is None:
+            v = float(self.lower_bound)
+            self.__dict__["_lower_f"] = v
+        return v
+
     def inverse_transform(self, value):
         return inv_softplus(torch.as_tensor(value) - self.lower_bound)
 

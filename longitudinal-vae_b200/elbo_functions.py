@@ -69,10 +69,27 @@ def _noise_of(likelihood, L, dtype, device):
     return src.noise.reshape(-1).to(dtype=dtype, device=device).expand(L)
 
 
+def _noise_entry(likelihood):
+    """The likelihood noise as a lazy Raw reference when its transform is known (packed evaluation with the kernel
+    hyper-parameters, spec.build_structure), else the evaluated tensor."""
+    from .constraints import GreaterThan, Positive
+    from .spec import Raw
+    src = getattr(likelihood, "noise_covar", likelihood)
+    con = getattr(src, "raw_noise_constraint", None)
+    if hasattr(src, "raw_noise") and type(con) in (GreaterThan, Positive):
+        return Raw(src.raw_noise, "softplus", con.lower_float())
+    if hasattr(src, "_log_noise") and hasattr(src, "min_log_noise"):
+        from .GP_model import _min_float
+        return Raw(src._log_noise, "bounded", _min_float(src, "min_log_noise"))
+    return src.noise.reshape(-1)
+
+
 class _KldBound(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mu, log_v, m, H, lengthscale, outputscale, noise, meta):
+    def forward(ctx, mu, log_v, m, H, hyper, meta):
+        """hyper: [n_ls + n_comp + 1, L] = lengthscales | outputscales | noise (constrained values)."""
         st = meta["structure"]
+        lengthscale, outputscale, noise = hyper[:st.n_ls], hyper[st.n_ls:st.n_ls + st.n_comp], hyper[st.n_ls + st.n_comp]
         x, z, offsets = meta["x"], meta["z"], meta["offsets"]
         L, M, Q = meta["L"], H.shape[-1], x.shape[1]
         if meta.get("counts") is not None:            # ragged minibatch: rows per subject known on the host
@@ -108,7 +125,8 @@ class _KldBound(torch.autograd.Function):
         d_m = d_H = None
         if not ctx.ng:
             d_m, d_H = g * c.grad_m.view(ctx.mshape), g * c.grad_H
-        return (g * c.d_mu, g * c.d_log_v, d_m, d_H, g * c.d_lengthscale, g * c.d_outputscale, g * c.d_noise, None)
+        d_mu, d_lv, d_hyp = torch._foreach_mul([c.d_mu, c.d_log_v, c.d_hyper], g)       # one grouped launch
+        return (d_mu, d_lv, d_m, d_H, d_hyp, None)
 
 
 def _structure_of(covar_module0, covar_module1, L, device):
@@ -121,13 +139,16 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
         raise RuntimeError("lvae_b200: the GP-prior ELBO op needs CUDA tensors (no CPU fallback)")
     L = latent_dim
     f64 = torch.float64
-    st, ls, os_ = _structure_of(covar_module0, covar_module1, L, x.device)
-    noise = _noise_of(likelihood, L, f64, x.device)
+    st, ls, os_, nz = build_structure(flatten(covar_module0), flatten(covar_module1), L, device=x.device,
+                                      extra=[_noise_entry(likelihood)])
+    # one [n_ls + n_comp + 1, L] table; when the packed transform produced it, the three parts are views of one tensor
+    same = ls._base is not None and ls._base is os_._base and ls._base is nz._base and ls._base.shape[0] == st.n_ls + st.n_comp + 1
+    hyper = ls._base if same else torch.cat([ls, os_, nz.reshape(1, L).to(f64)])
     if z.dim() == 2:
         z = z.unsqueeze(0).expand(L, -1, -1)
     meta = dict(structure=st, x=x.to(f64), z=z.to(f64), offsets=offsets, L=L, T_max=int(T_max), sum_T2=int(sum_T2),
                 scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient), counts=counts)
-    kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), ls, os_, noise, meta)
+    kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), hyper, meta)
     if natural_gradient:
         gH._lvae_hinv = meta.get("Hinv")
         return kld, gm, gH

@@ -11,7 +11,16 @@ from torch.nn import ModuleList
 
 from . import ops
 from .constraints import Positive
-from .spec import FlatComponent, build_structure, flatten, latent_count
+from .constraints import GreaterThan
+from .spec import FlatComponent, Raw, build_structure, flatten, latent_count
+
+
+def _lazy(raw, constraint, evaluated):
+    """A Raw reference when the constraint is the plain softplus + lower bound (packed evaluation, spec.build_structure),
+    otherwise the evaluated tensor."""
+    if type(constraint) in (GreaterThan, Positive):
+        return Raw(raw, "softplus", constraint.lower_float())
+    return evaluated()
 
 
 class LazyKernelTensor:
@@ -31,7 +40,7 @@ def evaluate_dense(kernel, x1, x2):
     gives [L,n1,n2] | [P,L,n1,n2]; un-batched kernels (no latent batch) give [n1,n2]."""
     comps = flatten(kernel)
     L = latent_count(comps, default=1)
-    batched = any(t is not None and torch.is_tensor(t) and t.numel() > 1
+    batched = any(t is not None and (torch.is_tensor(t) or isinstance(t, Raw)) and t.numel() > 1
                   for c in comps for t in [c.outputscale] + [f[2] for f in c.factors]) or \
         len(getattr(kernel, "batch_shape", ())) > 0
     dev = x1.device
@@ -120,7 +129,8 @@ class RBFKernel(Kernel):
     has_lengthscale = True
 
     def _flat_components(self):
-        return [FlatComponent(None, [('rbf', self._dim(), self.lengthscale.reshape(-1))])]
+        return [FlatComponent(None, [('rbf', self._dim(), _lazy(self.raw_lengthscale, self.raw_lengthscale_constraint,
+                                                               lambda: self.lengthscale.reshape(-1)))])]
 
 
 class ScaleKernel(Kernel):
@@ -143,7 +153,8 @@ class ScaleKernel(Kernel):
         self.initialize(outputscale=value)
 
     def _flat_components(self):
-        scale = FlatComponent(self.outputscale.reshape(-1), [])
+        scale = FlatComponent(_lazy(self.raw_outputscale, self.raw_outputscale_constraint,
+                                    lambda: self.outputscale.reshape(-1)), [])
         return [scale.times(c) for c in flatten(self.base_kernel)]
 
 

@@ -99,7 +99,10 @@ class KldCall:
         self.kld_per_latent = e(L)
         self.grad_m, self.grad_H = e(L, M), e(L, M, M)
         self.d_mu, self.d_log_v = e(N_b, L), e(N_b, L)
-        self.d_lengthscale, self.d_outputscale, self.d_noise = e(structure.n_ls, L), e(structure.n_comp, L), e(L)
+        self.d_hyper = e(structure.n_ls + structure.n_comp + 1, L)      # d/d [lengthscales | outputscales | noise], one buffer
+        self.d_lengthscale = self.d_hyper[:structure.n_ls]
+        self.d_outputscale = self.d_hyper[structure.n_ls:structure.n_ls + structure.n_comp]
+        self.d_noise = self.d_hyper[structure.n_ls + structure.n_comp]
         self.info = torch.zeros(4, dtype=torch.int32, device=dev)
         self.ks, self._keep = make_spec(structure)
         p = KldProblemT()
@@ -190,7 +193,7 @@ class SplitKldCall:
             self.parts.append((call, torch.from_numpy(rows).to(self.device), offs))
         a = self.parts[0][0]
         self.kld_per_latent, self.grad_m, self.grad_H = a.kld_per_latent, a.grad_m, a.grad_H
-        self.d_lengthscale, self.d_outputscale, self.d_noise = a.d_lengthscale, a.d_outputscale, a.d_noise
+        self.d_lengthscale, self.d_outputscale, self.d_noise, self.d_hyper = a.d_lengthscale, a.d_outputscale, a.d_noise, a.d_hyper
         self.stats, self.Hinv, self.info = a.stats, a.Hinv, a.info
         self.d_mu = torch.empty(self.N_b, L, dtype=F64, device=self.device)
         self.d_log_v = torch.empty(self.N_b, L, dtype=F64, device=self.device)
