@@ -9,7 +9,8 @@ from lvae_b200.training import natural_gradient_step
 from helpers import build_modules
 import numpy as np
 
-P, L, M = 1000, 32, 60
+import os
+P, L, M = int(os.environ.get("E2E_P", "1000")), 32, 60
 b = synth.make_batch("cfg2", P=P, L=L, M=M)
 dev = "cuda"
 cm0, cm1, lik = build_modules(b.lists, L, np.full((4, L), 2.5), np.full((5, L), 0.69), np.ones(L), dev)
@@ -56,4 +57,4 @@ import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
 for _ in range(20): step()
 pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pstats.Stats(pr).sort_stats("tottime").print_stats(35)
