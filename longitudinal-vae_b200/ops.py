@@ -11,7 +11,10 @@ F64 = torch.float64
 
 
 def _c(t):
-    return t.detach().to(F64).contiguous()
+    t = t.detach()
+    if t.dtype is F64 and t.is_contiguous():         # the common case: nothing to convert (this runs ~20 times per step)
+        return t
+    return t.to(F64).contiguous()
 
 
 def kernel_dense(structure, lengthscale, outputscale, x1, x2, which="all", diag_add=None):
@@ -110,7 +113,7 @@ class KldCall:
         p.natural_gradient, p.path = int(bool(natural_gradient)), int(path)
         p.ks = self.ks
         self.stats_stride = int(self.lib.lvae_kld_stats_stride(M, structure.n_ls, structure.n_comp))
-        self.stats = torch.zeros(L, self.stats_stride, dtype=F64, device=dev)
+        self.stats = e(L, self.stats_stride)             # fully written by the reduce kernel of the subject pass
         self.workspace = e(int(self.lib.lvae_kld_workspace_doubles(C.byref(p))))
         for name in ("kld_per_latent", "grad_m", "grad_H", "d_mu", "d_log_v", "d_lengthscale", "d_outputscale",
                      "d_noise", "stats", "workspace", "info"):
