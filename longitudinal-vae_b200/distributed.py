@@ -79,15 +79,22 @@ def peer_stats(group, numel, device):
     return _PEER[key]
 
 
-def enable(group=None, exchange="nccl"):
-    """Route the statistics exchange of minibatch_KLD_upper_bound[_iter] through `group` (default: WORLD).
-    After this, every rank passes ITS rows; P_batch / P_in_current_batch remain the GLOBAL minibatch subject counts.
-    exchange: "nccl" (one all_reduce) | "p2p" (symmetric memory + lvae_peer_sum_f64, single node, see PeerStats)."""
+def enable(group=None, exchange="nccl", shard="subjects"):
+    """Route minibatch_KLD_upper_bound[_iter] through `group` (default: WORLD).
+    shard="subjects" (default): every rank passes ITS rows; P_batch / P_in_current_batch remain the GLOBAL minibatch subject
+        counts; the statistics row is summed over ranks.  exchange: "nccl" (one all_reduce) | "p2p" (symmetric memory +
+        lvae_peer_sum_f64, single node, see PeerStats).
+    shard="latents": every rank passes the SAME minibatch and computes latents latent_slice(L, rank, world) of the bound (for
+        minibatches too small to split by subject): kld_total comes back all-reduced, grad_m / grad_H all-gathered;
+        gradients w.r.t. mu, log_v and the hyper-parameters cover this rank's latent columns — sum them over ranks
+        (all_reduce) for the full gradient."""
     if not dist.is_initialized():
         raise RuntimeError("lvae_b200.distributed.enable: torch.distributed is not initialised")
     if exchange not in ("nccl", "p2p"):
         raise ValueError(exchange)
-    elbo_functions.set_process_group(group if group is not None else dist.group.WORLD, exchange)
+    if shard not in ("subjects", "latents"):
+        raise ValueError(shard)
+    elbo_functions.set_process_group(group if group is not None else dist.group.WORLD, exchange, shard)
 
 
 def disable():

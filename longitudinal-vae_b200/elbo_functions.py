@@ -20,12 +20,15 @@ _PENDING = []        # KldCall objects whose info flags have not been read yet (
 
 
 _EXCHANGE = "nccl"   # how the statistics row is summed over ranks: "nccl" all-reduce | "p2p" (distributed.PeerStats)
+_SHARD = "subjects"  # "subjects": every rank holds its rows of the minibatch | "latents": every rank holds its latent dimensions
 
 
-def set_process_group(group, exchange="nccl"):
-    """Shard mode: every rank passes ITS rows; P_batch / P_in_current_batch stay GLOBAL minibatch subject counts."""
-    global _GROUP, _EXCHANGE
-    _GROUP, _EXCHANGE = group, exchange
+def set_process_group(group, exchange="nccl", shard="subjects"):
+    """shard="subjects": every rank passes ITS rows; P_batch / P_in_current_batch stay GLOBAL minibatch subject counts.
+    shard="latents": every rank passes the SAME full minibatch and computes the bound for its own slice of the latent
+    dimensions (no statistics exchange: the latent dimensions are independent); see distributed.enable."""
+    global _GROUP, _EXCHANGE, _SHARD
+    _GROUP, _EXCHANGE, _SHARD = group, exchange, shard
 
 
 def exchange_stats(call, group, exchange):
@@ -101,7 +104,7 @@ class _KldBound(torch.autograd.Function):
         call.bind(x, offsets, mu, log_v, z, m.reshape(L, M), H, lengthscale, outputscale, noise, meta["scale"],
                   meta["const_term"], meta["eps"])
         call.head()
-        exchange_stats(call, _GROUP, _EXCHANGE)
+        exchange_stats(call, meta.get("group"), _EXCHANGE)
         call.tail()
         if _CHECK == "immediate":
             call.raise_on_info()
@@ -148,11 +151,53 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
         z = z.unsqueeze(0).expand(L, -1, -1)
     meta = dict(structure=st, x=x.to(f64), z=z.to(f64), offsets=offsets, L=L, T_max=int(T_max), sum_T2=int(sum_T2),
                 scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient), counts=counts)
+    if _GROUP is not None and _SHARD == "latents":
+        return _run_latent_shard(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), hyper, meta, natural_gradient)
+    meta["group"] = _GROUP
     kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), hyper, meta)
     if natural_gradient:
         gH._lvae_hinv = meta.get("Hinv")
         return kld, gm, gH
     return kld, None, None
+
+
+def latent_slice(L, rank, world):
+    """[l0, l1) of `rank` when L latent dimensions are dealt to `world` ranks in contiguous, balanced blocks."""
+    return (L * rank) // world, (L * (rank + 1)) // world
+
+
+def _run_latent_shard(mu, log_v, m, H, hyper, meta, natural_gradient):
+    """Latent-dimension sharding (the fallback for minibatches too small to split by subject, where the per-latent
+    M x M work dominates).  The latent dimensions of the bound are independent, so rank r runs the whole op on latents
+    [l0, l1) of the SAME minibatch: kld_total is all-reduced (its gradient reaches this rank's latent columns of mu, log_v and
+    of every hyper-parameter; summing the parameter gradients over ranks gives the full gradient), grad_m / grad_H are
+    all-gathered into full [L, ...] tensors."""
+    import torch.distributed as dist
+    L, M = meta["L"], H.shape[-1]
+    rank, world = dist.get_rank(_GROUP), dist.get_world_size(_GROUP)
+    if L < world:
+        raise RuntimeError(f"lvae_b200: latent sharding needs at least one latent dimension per rank (L={L}, ranks={world})")
+    l0, l1 = latent_slice(L, rank, world)
+    Ll = l1 - l0
+    sub = dict(meta)
+    sub.update(L=Ll, z=meta["z"][l0:l1].contiguous(), const_term=meta["const_term"] * Ll / L, group=None)
+    kld_l, gm_l, gH_l = _KldBound.apply(mu[:, l0:l1].contiguous(), log_v[:, l0:l1].contiguous(),
+                                        m.reshape(L, M, 1)[l0:l1].contiguous(), H[l0:l1].contiguous(),
+                                        hyper[:, l0:l1].contiguous(), sub)
+    tot = kld_l.detach().clone()
+    dist.all_reduce(tot, group=_GROUP)
+    kld = kld_l + (tot - kld_l.detach())                    # value: all latents; gradient: this rank's latents
+    if not natural_gradient:
+        return kld, None, None
+    Lmax = (L + world - 1) // world                          # blocks differ by at most one latent: pad to the largest
+    send = torch.zeros(Lmax, M * (M + 1), dtype=torch.float64, device=mu.device)
+    send[:Ll, :M] = gm_l.reshape(Ll, M)
+    send[:Ll, M:] = gH_l.reshape(Ll, M * M)
+    recv = torch.empty(world, Lmax, M * (M + 1), dtype=torch.float64, device=mu.device)
+    dist.all_gather_into_tensor(recv, send, group=_GROUP)
+    parts = [recv[r, :latent_slice(L, r, world)[1] - latent_slice(L, r, world)[0]] for r in range(world)]
+    full = torch.cat(parts)
+    return kld, full[:, :M].reshape(L, M, 1).contiguous(), full[:, M:].reshape(L, M, M).contiguous()
 
 
 def minibatch_KLD_upper_bound(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z, P_tot,

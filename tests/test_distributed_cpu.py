@@ -104,3 +104,14 @@ def test_sharded_statistics_sum_to_full_batch(tmp_path):
         kl = 0.5 * ((Ki * H.transpose(-1, -2)).sum() + (m * (Ki @ m)).sum() - L * M + torch.logdet(Kzz).sum() - torch.logdet(H).sum())
         kld = P_tot / P_b * 0.5 * (scal - D2 + E) + kl - L * P_tot * T / 2
     assert abs(kld.item() - float(g["kld"])) <= 1e-7 * abs(float(g["kld"]))
+
+
+def test_latent_slices_partition_the_latent_dimensions():
+    """shard="latents": contiguous, balanced blocks that cover 0..L-1 exactly once (host logic of distributed.enable)."""
+    from lvae_b200.elbo_functions import latent_slice
+    for L, world in [(32, 8), (5, 2), (7, 3), (64, 8), (3, 3), (10, 4)]:
+        blocks = [latent_slice(L, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == L
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        sizes = [b - a for a, b in blocks]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1

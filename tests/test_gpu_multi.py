@@ -68,3 +68,66 @@ def test_two_rank_sharding_matches_reference(case, exchange, tmp_path):
     assert outs[0]["hi"] == outs[1]["lo"]
     if exchange == "p2p":        # rank-ordered sums: the replicated tail gives bit-identical results on both ranks
         assert outs[0]["kld"] == outs[1]["kld"] and torch.equal(outs[0]["gH"], outs[1]["gH"])
+
+
+def _worker_latent(rank, world, port, case, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200 import distributed as D
+    from helpers import build_modules
+    g = load_golden(case)
+    dev = f"cuda:{rank}"
+    L = g["mu"].shape[1]
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    cm0, cm1, lik = build_modules(g["lists"], L, g["lengthscale"], g["outputscale"], g["noise"], dev)
+    mu = t("mu").clone().requires_grad_(True)
+    lv = t("log_v").clone().requires_grad_(True)
+    P_b = len(g["offsets"]) - 1
+    D.enable(shard="latents")
+    if bool(g["ragged"]):
+        kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, t("m"), t("H"), t("x"), mu, lv, t("z"),
+                                                        int(g["P_tot"]), P_b, int(g["N_tot"]), True, 2, float(g["eps"]))
+    else:
+        kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, t("m"), t("H"), t("x"), mu, lv, t("z"),
+                                                   int(g["P_tot"]), P_b, int(g["T"]), True, float(g["eps"]))
+    kld.sum().backward()
+    D.disable()
+    l0, l1 = EF.latent_slice(L, rank, world)
+    own = torch.zeros(L, dtype=torch.bool)
+    own[l0:l1] = True
+    local_only = bool((mu.grad[:, ~own.to(dev)] == 0).all())        # gradients only reach this rank's latent columns
+    dist.all_reduce(mu.grad)
+    dist.all_reduce(lv.grad)
+    for p in list(cm0.parameters()) + list(cm1.parameters()) + list(lik.parameters()):
+        dist.all_reduce(p.grad)
+    from helpers import constrained_param_grads
+    torch.save(dict(kld=float(kld.sum().item()), gm=gm.cpu(), gH=gH.cpu(), d_mu=mu.grad.cpu(), d_lv=lv.grad.cpu(),
+                    local_only=local_only, d_hyper=constrained_param_grads(cm0, cm1, lik)), os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["cfg2_small", "cfg4_ragged", "cfg3_small"])
+def test_two_rank_latent_sharding_matches_reference(case, tmp_path):
+    """shard="latents": both ranks see the whole minibatch, each computes its latent dimensions; kld all-reduced, natural
+    gradients all-gathered, parameter gradients summed over ranks equal the single-GPU / reference values."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from helpers import golden_hyper_vector, rel
+    mp.spawn(_worker_latent, args=(2, 29500 + os.getpid() % 200, case, str(tmp_path)), nprocs=2, join=True)
+    g = load_golden(case)
+    ref = golden_hyper_vector(g)
+    for r in range(2):
+        o = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"), weights_only=False)
+        assert o["local_only"]
+        assert abs(o["kld"] - float(g["kld"])) <= 1e-6 * abs(float(g["kld"]))
+        assert rel(o["gm"], g["grad_m"]) < 1e-6 and rel(o["gH"], g["grad_H"]) < 1e-6
+        assert rel(o["d_mu"], g["d_mu"]) < 1e-6 and rel(o["d_lv"], g["d_log_v"]) < 1e-6
+        assert np.abs(o["d_hyper"] - ref).max() <= 1e-6 * np.abs(ref).max()
