@@ -34,9 +34,6 @@ int lvae_gemm(const GemmDesc& d, cudaStream_t st);
 // Padded order used by the blocked factorisations: 128 or 256 (matrices are identity-padded).
 static inline int lvae_pad_order(int n) { return n <= 128 ? 128 : 256; }
 
-// Workspace (doubles) for lvae_potrf_big / lvae_spd_inverse_big on `batch` matrices of padded order np.
-int64_t lvae_big_scratch_doubles(int np, int batch);
-
 // In-place blocked lower Cholesky of `batch` identity-padded np x np matrices (row stride np, matrix stride np*np).
 // The strict upper triangle is NOT cleared.  dinv: [batch][np/64][64*64] receives the inverses of the diagonal blocks of
 // the factor.  info_slot[index / info_mod] (info_mod > 0; else info_slot[0]) is set to 1 + (index % info_mod) of the first

@@ -109,36 +109,6 @@ __device__ __forceinline__ double comp_value(const DevSpec& s, int c, const doub
     return f;
 }
 
-// Branch-free evaluation of one component for ONE row against TWO columns (the two accumulator columns of a DMMA lane):
-// row-side loads and the per-component constants are shared, no divergent control flow, exp always evaluated.
-__device__ __forceinline__ void comp_pair(const DevSpec& s, int c, const double* __restrict__ xa,
-                                          const double* __restrict__ xb0, const double* __restrict__ xb1,
-                                          const double* __restrict__ half_inv_l2, const double* __restrict__ etab,
-                                          double& f0, double& f1, double& d20, double& d21) {
-    bool on0 = true, on1 = true;
-#pragma unroll
-    for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
-        if (i < s.n_mask[c]) {
-            const int dm = s.mask_dim[c][i];
-            const double a = xa[dm], b0 = xb0[dm], b1 = xb1[dm];
-            if (s.mask_type[c][i] == LVAE_CAT) { on0 = on0 && (a - b0 == 0.0); on1 = on1 && (a - b1 == 0.0); }
-            else { on0 = on0 && (a + b0 == 2.0); on1 = on1 && (a + b1 == 2.0); }
-        }
-    }
-    double e0 = 1.0, e1 = 1.0;
-    d20 = 0.0; d21 = 0.0;
-    const int rd = s.rbf_dim[c];
-    if (rd >= 0) {
-        const double h = half_inv_l2[s.ls_idx[c]], a = xa[rd];
-        const double t0 = a - xb0[rd], t1 = a - xb1[rd];
-        d20 = t0 * t0; d21 = t1 * t1;
-        e0 = exp_neg(-d20 * h, etab);
-        e1 = exp_neg(-d21 * h, etab);
-    }
-    f0 = on0 ? e0 : 0.0;
-    f1 = on1 ? e1 : 0.0;
-}
-
 // single-element branch-free variant
 __device__ __forceinline__ double comp_one(const DevSpec& s, int c, const double* __restrict__ xa,
                                            const double* __restrict__ xb, const double* __restrict__ half_inv_l2,
