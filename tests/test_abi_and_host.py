@@ -152,3 +152,52 @@ def test_split_call_row_mapping_and_decision():
     assert not decide(60, [5, 40], path=1) and not decide(60, [1] + [40] * 50)
     src = open(ops.__file__).read()
     assert "counts[short].sum() >= 0.1 * counts.sum()" in src and "counts.max() > 24" in src   # the rule tested above is the shipped one
+
+
+def test_packed_hyper_parameters_match_module_properties():
+    """spec.build_structure evaluates all lengthscales / outputscales / noise with ONE stack + ONE transform (spec.Raw); values
+    and gradients w.r.t. every raw parameter must equal the per-module constraint transforms (gpytorch-style softplus + lower
+    bound, and GP_model.py's exp(min + softplus(raw - min)))."""
+    from lvae_b200 import synth, GP_model as GM
+    from lvae_b200.elbo_functions import _noise_entry
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200.likelihoods import GaussianLikelihood
+    from lvae_b200.constraints import GreaterThan
+    from lvae_b200.gp_kernels import RBFKernel
+    from lvae_b200.spec import build_structure, flatten
+    L = 3
+    lists = synth.kernel_lists(synth.CONFIGS["cfg4"]) if hasattr(synth, "CONFIGS") else synth.make_batch("cfg4", P=2, L=L, M=4).lists
+    torch.manual_seed(0)
+    for style in ("gpytorch", "gp_model"):
+        if style == "gpytorch":
+            cm0, cm1 = generate_kernel_batched(L, **lists, id_covariate=2)
+            lik = GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=GreaterThan(1e-8))
+        else:
+            cm0, cm1 = GM.generate_kernel_batched(L, **lists, id_covariate=2)
+            lik = GM.Likelihoods(L, 1.0)
+        mods = [cm0.double(), cm1.double(), lik.double()]
+        params = [p for m_ in mods for p in m_.parameters()]
+        with torch.no_grad():
+            for p in params:
+                p.add_(0.3 * torch.randn_like(p))
+        st, ls, os_, nz = build_structure(flatten(cm0), flatten(cm1), L, device="cpu", extra=[_noise_entry(lik)])
+        assert ls._base is not None and ls._base is os_._base and ls._base is nz._base          # the packed path was taken
+        # reference values straight from the module properties
+        ref_os, ref_ls = [], []
+        for mod in (cm0, cm1):
+            for sk in mod.kernels:
+                ref_os.append((sk.outputscale if style == "gpytorch" else sk.scale).reshape(-1))
+                for sub in sk.modules():
+                    if isinstance(sub, RBFKernel) or isinstance(sub, GM.RbfKernel):
+                        ref_ls.append(sub.lengthscale.reshape(-1))
+        ref_noise = (lik.noise_covar.noise if style == "gpytorch" else lik.noise).reshape(-1)
+        assert torch.allclose(os_, torch.stack(ref_os), rtol=1e-14, atol=0) and torch.allclose(ls, torch.stack(ref_ls), rtol=1e-14, atol=0)
+        assert torch.allclose(nz.reshape(-1), ref_noise, rtol=1e-14, atol=0)
+        w = torch.randn(ls._base.shape, dtype=torch.float64)
+        g1 = torch.autograd.grad((ls._base * w).sum(), params, allow_unused=True)
+        ref_table = torch.cat([torch.stack(ref_ls), torch.stack(ref_os), ref_noise.reshape(1, L)])
+        g2 = torch.autograd.grad((ref_table * w).sum(), params, allow_unused=True)
+        for a, b in zip(g1, g2):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert torch.allclose(a, b, rtol=1e-13, atol=1e-300)
