@@ -187,7 +187,7 @@ __host__ __device__ inline size_t uv_doubles(int MP, int Q) {
 }
 
 template <int NTW>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, NTW <= 2 ? 3 : 2)
 k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b,
      const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ z, const double* __restrict__ ls,
      const double* __restrict__ os, double c, double* __restrict__ d_mu, double* __restrict__ ws) {
