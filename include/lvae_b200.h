@@ -71,6 +71,23 @@ int lvae_kernel_blocks_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int
                            const double* lengthscale, const double* outputscale, const double* diag_add, double* out,
                            void* stream);
 
+/* Hyper-parameter adjoints of the two functions above — what autograd through gpytorch's ScaleKernel / RBFKernel
+ * (kernel_spec.py:58-69, GP_model.py:55-110) delivers in the reference when deviance_upper_bound / elbo
+ * (elbo_functions.py:36-142) are trained on (training.py:326-343, 533-548, 654, 730).  grad_out has the layout of `out`.
+ *   d_outputscale[c][l] = sum grad_out * k_c / outputscale[c][l]            (rows outside comp_begin..comp_end: 0)
+ *   d_lengthscale[r][l] = sum grad_out * k_c * d^2 / lengthscale[r][l]^3     over the components that use row r
+ *   d_diag_add[l]       = sum_i grad_out[., i, i]                            (skipped when NULL)
+ * All three are overwritten, [rows, L] like the inputs; sums run in a fixed order (bitwise reproducible). */
+int lvae_kernel_dense_bwd_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int32_t comp_end, int32_t L,
+                              int32_t n_batch, int32_t Q, const double* x1, int64_t x1_latent_stride, int32_t n1,
+                              const double* x2, int64_t x2_latent_stride, int32_t n2, const double* lengthscale,
+                              const double* outputscale, const double* grad_out, double* d_lengthscale,
+                              double* d_outputscale, double* d_diag_add, void* stream);
+int lvae_kernel_blocks_bwd_f64(const lvae_kernel_spec_t* ks, int32_t comp_begin, int32_t comp_end, int32_t L, int32_t Q,
+                               const double* x, const int32_t* offsets, int32_t P_b, int64_t block_stride,
+                               const double* lengthscale, const double* outputscale, const double* grad_out,
+                               double* d_lengthscale, double* d_outputscale, double* d_diag_add, void* stream);
+
 /* Batched GEMM on the FP64 tensor pipe: C[b] (m x n) = alpha * op(A[b]) op(B[b]) + beta * C[b], row-major — replaces the
  * torch.matmul / einsum contractions of elbo_functions.py:183-184,189,194,208-214 when M > 64.
  * op(A) is m x k: trans_a == 0 reads A[i*lda + kk], else A[kk*lda + i]; likewise op(B) (k x n).

@@ -55,7 +55,8 @@ class _DenseModule(nn.Module):
         structure, ls, os_ = build_structure(comps, [], L, device=x1.device)
         a = x1 if x1.dim() < 3 or x1.shape[0] == L else x1.expand(L, *x1.shape[-2:])
         b = x2 if x2.dim() < 3 or x2.shape[0] == L else x2.expand(L, *x2.shape[-2:])
-        return ops.kernel_dense(structure, ls, os_, a, b, "all")
+        from .diff_ops import KernelDense
+        return KernelDense.apply(structure, "all", a, b, ls, os_, None)
 
 
 class BinKernel(_DenseModule):

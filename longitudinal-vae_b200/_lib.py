@@ -18,7 +18,8 @@ CAT, BIN = 0, 1
 EXPORTS = ["lvae_kernel_dense_f64", "lvae_kernel_blocks_f64", "lvae_potrf_batched_f64", "lvae_potri_batched_f64",
            "lvae_kld_stats_stride", "lvae_kld_workspace_doubles", "lvae_kld_head_f64", "lvae_kld_subjects_f64",
            "lvae_kld_tail_f64", "lvae_kld_minibatch_f64", "lvae_ng_step_f64", "lvae_launch_count", "lvae_version",
-           "lvae_profile_enable", "lvae_profile_last_ms", "lvae_debug_exp_neg_f64", "lvae_kld_hinv_offset", "lvae_gemm_batched_f64", "lvae_ng_workspace_doubles", "lvae_peer_sum_f64"]
+           "lvae_profile_enable", "lvae_profile_last_ms", "lvae_debug_exp_neg_f64", "lvae_kld_hinv_offset", "lvae_gemm_batched_f64", "lvae_ng_workspace_doubles", "lvae_peer_sum_f64",
+           "lvae_kernel_dense_bwd_f64", "lvae_kernel_blocks_bwd_f64"]
 
 _dp = C.c_void_p
 
@@ -57,6 +58,10 @@ def load():
     pp = C.POINTER(KldProblemT)
     lib.lvae_kernel_dense_f64.argtypes = [ksp, i32, i32, i32, i32, i32, vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp]
     lib.lvae_kernel_blocks_f64.argtypes = [ksp, i32, i32, i32, i32, vp, vp, i32, i64, vp, vp, vp, vp, vp]
+    lib.lvae_kernel_dense_bwd_f64.argtypes = [ksp, i32, i32, i32, i32, i32, vp, i64, i32, vp, i64, i32, vp, vp, vp, vp, vp,
+                                              vp, vp]
+    lib.lvae_kernel_blocks_bwd_f64.argtypes = [ksp, i32, i32, i32, i32, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.lvae_kernel_dense_bwd_f64.restype = lib.lvae_kernel_blocks_bwd_f64.restype = C.c_int
     lib.lvae_potrf_batched_f64.argtypes = [vp, i32, i64, i32, vp, vp]
     lib.lvae_potri_batched_f64.argtypes = [vp, vp, i32, i64, i32, vp]
     lib.lvae_gemm_batched_f64.argtypes = [i32, i32, i32, i32, i32, dbl, vp, i32, i64, vp, i32, i64, dbl, vp, i32, i64, i32,

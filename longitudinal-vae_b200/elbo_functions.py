@@ -244,19 +244,26 @@ def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, lat
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# the non-minibatch bounds of elbo_functions.py:8-142 and validation.py:8-68, FORWARD ONLY (evaluation /
-# validation use; they carry no autograd graph — training through them is not provided, the Hensman path above is).
-# Kernel matrices from lvae_kernel_dense_f64 / lvae_kernel_blocks_f64, Cholesky factors and explicit inverses from
-# lvae_potrf_batched_f64 / lvae_potri_batched_f64, the M x M contractions from the batched DMMA GEMM.
+# the non-minibatch bounds of elbo_functions.py:8-142 and validation.py:8-68.  Like the reference's, the values
+# are autograd graph nodes w.r.t. the variational mean / log-variance (or the latent sample), every kernel hyper-parameter
+# and the likelihood noise, so the loops that minimise them (training.py:326-343, 533-548, 654, 730) work unchanged; the
+# covariates and inducing inputs are constants (LVAE.py:204-208).  Kernel matrices and their hyper-parameter adjoints come
+# from lvae_kernel_dense/blocks[_bwd]_f64, inverses and log-determinants from lvae_potrf/potri_batched_f64, the
+# contractions from the batched DMMA GEMM (diff_ops.py); the element-wise glue between them is plain torch.
 # ---------------------------------------------------------------------------------------------------------------
-def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps):
-    """Shared pieces of elbo / deviance_upper_bound: per latent l (everything detached, FP64, on x's device):
-    K0xz [L,N,M], iKzz, iB [L*P,T,T], iB_K0xz [L,N,M], S = K0zx iB K0xz, iW = (Kzz + S)^-1, the three log-dets, tr."""
+def _need_cuda(x):
     if not x.is_cuda:
         raise RuntimeError("lvae_b200: the GP-prior bounds need CUDA tensors (no CPU fallback)")
+
+
+def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps):
+    """Shared pieces of elbo / deviance_upper_bound, per latent l (FP64, on x's device):
+    K0xz [L,N,M], iB [L*P,T,T], iB_K0xz [L,N,M], S = K0zx iB K0xz, iW = (Kzz + S)^-1, the summed log-dets, tr."""
+    from . import diff_ops as D
+    _need_cuda(x)
     f64 = torch.float64
-    x = x.to(f64).contiguous()
-    z = z.to(f64)
+    x = x.detach().to(f64).contiguous()
+    z = z.detach().to(f64)
     if z.dim() == 2:
         z = z.unsqueeze(0).expand(L, -1, -1)
     z = z.contiguous()
@@ -264,64 +271,62 @@ def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps
     if N != P * T:
         raise RuntimeError(f"shape '[{P}, {T}, {x.shape[1]}]' is invalid for input of size {x.numel()}")
     st, ls, os_ = _structure_of(covar_module0, covar_module1, L, x.device)
-    ls, os_ = ls.detach(), os_.detach()
-    noise = _noise_of(likelihood, L, f64, x.device).detach().contiguous()
+    noise = _noise_of(likelihood, L, f64, x.device).contiguous()
     offsets = torch.arange(0, N + 1, T, dtype=torch.int32, device=x.device)
     eye = torch.eye(M, dtype=f64, device=x.device)
-    K0xz = ops.kernel_dense(st, ls, os_, x, z, "k0")
-    K0zz = ops.kernel_dense(st, ls, os_, z, z, "k0") + eps * eye
-    K0_st = ops.kernel_blocks(st, ls, os_, x, offsets, P * T * T, "k0").reshape(L * P, T, T)
-    B_st = ops.kernel_blocks(st, ls, os_, x, offsets, P * T * T, "k1", diag_add=noise).reshape(L * P, T, T)
-    LK = ops.potrf_batched(K0zz)
-    iK = ops.potri_batched(LK)
-    LB = ops.potrf_batched(B_st)
-    iB = ops.potri_batched(LB)
-    iB_K0xz = torch.bmm(iB, K0xz.reshape(L * P, T, M)).reshape(L, N, M)
-    S = ops.gemm_batched(K0xz, iB_K0xz, trans_a=True)
+    K0xz = D.KernelDense.apply(st, "k0", x, z, ls, os_, None)
+    K0zz = D.KernelDense.apply(st, "k0", z, z, ls, os_, None) + eps * eye
+    K0_st = D.KernelBlocks.apply(st, "k0", x, offsets, P * T * T, ls, os_, None).reshape(L * P, T, T)
+    B_st = D.KernelBlocks.apply(st, "k1", x, offsets, P * T * T, ls, os_, noise).reshape(L * P, T, T)
+    iK, ldK = D.spd_inverse(K0zz)
+    iB, ldB = D.spd_inverse(B_st)
+    iB_K0xz = D.gemm(iB, K0xz.reshape(L * P, T, M)).reshape(L, N, M)
+    S = D.gemm(K0xz, iB_K0xz, ta=True)
     W = K0zz + S
     W = 0.5 * (W + W.transpose(1, 2))
-    LW = ops.potrf_batched(W)
-    iW = ops.potri_batched(LW)
-    logdet = lambda Lc, n: 2.0 * torch.log(torch.diagonal(Lc, dim1=-2, dim2=-1)).reshape(L, -1).sum(1)
-    logDet = -logdet(LK, M) + logdet(LB, T) + logdet(LW, M)
+    iW, ldW = D.spd_inverse(W)
+    logDet = -ldK + ldB.reshape(L, P).sum(1) + ldW
     tr = (iB * K0_st).reshape(L, -1).sum(1) - (S * iK).reshape(L, -1).sum(1)
     return dict(K0xz=K0xz, iB=iB, iB_K0xz=iB_K0xz, iW=iW, logDet=logDet, tr=tr, N=N, M=M)
 
 
 def _quad_form(t, y, L, P, T):
     """qF = y^T B^-1 y - p^T W^-1 p with p = K0zx B^-1 y, per latent; y [L,N]."""
-    iB_y = torch.bmm(t["iB"], y.reshape(L * P, T, 1)).reshape(L, -1)
+    from . import diff_ops as D
+    iB_y = D.gemm(t["iB"], y.reshape(L * P, T, 1)).reshape(L, -1)
     qF1 = (y * iB_y).sum(1)
-    p = torch.bmm(t["K0xz"].transpose(1, 2), iB_y.unsqueeze(2))
-    qF2 = (p * torch.bmm(t["iW"], p)).reshape(L, -1).sum(1)
+    p = D.gemm(t["K0xz"], iB_y.unsqueeze(2), ta=True)
+    qF2 = (p * D.gemm(t["iW"], p)).reshape(L, -1).sum(1)
     return qF1 - qF2
 
 
 def _dubo_per_latent(L, covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, P, T, eps):
     """elbo_functions.py:90-142 / validation.py:8-68 for all latents at once; m, log_v [N,L] (or [N] for L = 1)."""
+    from . import diff_ops as D
     t = _low_rank_terms(L, covar_module0, covar_module1, likelihood, train_xt, z, P, T, eps)
     f64 = torch.float64
-    mL = m.detach().to(f64).reshape(t["N"], L).t().contiguous()
-    lv = log_v.detach().to(f64).reshape(t["N"], L).t().contiguous()
+    mL = m.to(f64).reshape(t["N"], L).t().contiguous()
+    lv = log_v.to(f64).reshape(t["N"], L).t().contiguous()
     v = torch.exp(lv)
     qF = _quad_form(t, mL, L, P, T)
     tr_iB_D = (torch.diagonal(t["iB"], dim1=-2, dim2=-1).reshape(L, -1) * v).sum(1)
     D05 = t["iB_K0xz"] * torch.sqrt(v).unsqueeze(2)
-    SD = ops.gemm_batched(D05, D05, trans_a=True, flags=3)                       # K0zx B^-1 D B^-1 K0xz (symmetric)
+    SD = D.gemm(D05, D05, ta=True, flags=3)                                      # K0zx B^-1 D B^-1 K0xz (symmetric)
     tr_iSigma_D = tr_iB_D - (t["iW"] * SD).reshape(L, -1).sum(1)
     return 0.5 * (tr_iSigma_D + qF - P * T + t["logDet"] - lv.sum(1) + t["tr"])
 
 
 def deviance_upper_bound(covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, P, T, eps):
-    """DUBO of one latent dimension with un-batched kernels (elbo_functions.py:90-142).  Forward only (see above)."""
+    """DUBO of one latent dimension with un-batched kernels (elbo_functions.py:90-142); differentiable (see above)."""
     return _dubo_per_latent(1, covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, P, T, eps).reshape(())
 
 
 def elbo(covar_module0, covar_module1, likelihood, train_xt, train_yt, z, P, T, eps):
-    """Low-rank evidence lower bound of one latent dimension given a latent sample (elbo_functions.py:36-88).  Forward only."""
+    """Low-rank evidence lower bound of one latent dimension given a latent sample (elbo_functions.py:36-88);
+    differentiable w.r.t. the sample, the kernel hyper-parameters and the noise."""
     import math
     t = _low_rank_terms(1, covar_module0, covar_module1, likelihood, train_xt, z, P, T, eps)
-    y = train_yt.detach().to(torch.float64).reshape(1, t["N"])
+    y = train_yt.to(torch.float64).reshape(1, t["N"])
     qF = _quad_form(t, y, 1, P, T)
     logLike = -0.5 * T * P * math.log(2 * math.pi) - 0.5 * (t["logDet"] + qF)
     return (logLike - 0.5 * t["tr"]).reshape(())
@@ -329,19 +334,18 @@ def elbo(covar_module0, covar_module1, likelihood, train_xt, train_yt, z, P, T, 
 
 def KL_closed(covar_module, train_x, likelihoods, data, mu, log_var):
     """Closed-form KL[q || GP prior] with the dense N x N kernel (elbo_functions.py:8-34); N <= 256 (the batched Cholesky's
-    limit — the reference uses this for small exact checks only).  Forward only."""
+    limit — the reference uses this for small exact checks only).  Differentiable like the two bounds above."""
+    from . import diff_ops as D
     f64 = torch.float64
-    if not train_x.is_cuda:
-        raise RuntimeError("lvae_b200: the GP-prior bounds need CUDA tensors (no CPU fallback)")
+    _need_cuda(train_x)
     N = data.shape[0]
-    x = train_x.to(f64)
-    noise = _noise_of(likelihoods, 1, f64, x.device).detach()
+    x = train_x.detach().to(f64)
+    noise = _noise_of(likelihoods, 1, f64, x.device)
     K1 = covar_module(x, x).evaluate().reshape(N, N) + noise * torch.eye(N, dtype=f64, device=x.device)
-    LK = ops.potrf_batched(K1.unsqueeze(0))
-    iK = ops.potri_batched(LK)[0]
-    mu1 = mu.detach().to(f64).reshape(-1)
-    v1 = torch.exp(log_var.detach().to(f64).reshape(-1))
-    logdet11 = 2.0 * torch.log(torch.diagonal(LK[0])).sum()
+    iK, logdet11 = D.spd_inverse(K1.unsqueeze(0))
+    iK = iK[0]
+    mu1 = mu.to(f64).reshape(-1)
+    lv1 = log_var.to(f64).reshape(-1)
     qf1 = (mu1 * (iK @ mu1)).sum()
-    tr1 = (v1 * torch.diagonal(iK)).sum()
-    return 0.5 * (tr1 + qf1 - N + logdet11 - log_var.detach().to(f64).sum())
+    tr1 = (torch.exp(lv1) * torch.diagonal(iK)).sum()
+    return 0.5 * (tr1 + qf1 - N + logdet11.sum() - lv1.sum())

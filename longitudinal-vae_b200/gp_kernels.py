@@ -4,7 +4,8 @@ The reference builds its kernels from `gpytorch.kernels.{Kernel, RBFKernel, Scal
 (kernel_spec.py:2-3, kernel_gen.py:3).  GPyTorch is a third-party dependency that this package does not require: the
 classes below keep the attribute names the reference relies on (`kernels`, `base_kernel`, `outputscale`, `lengthscale`,
 `active_dims`, `raw_*` parameters with softplus constraints, `k1 * k2`, `k0 + k1`, `module(x1, x2).evaluate()`), but hold
-no dense torch arithmetic — `.evaluate()` flattens the tree (spec.py) and runs lvae_kernel_dense_f64 on the GPU.
+no dense torch arithmetic — `.evaluate()` flattens the tree (spec.py) and runs lvae_kernel_dense_f64 on the GPU
+(lvae_kernel_dense_bwd_f64 under autograd).
 """
 import torch
 from torch.nn import ModuleList
@@ -37,7 +38,9 @@ class LazyKernelTensor:
 
 def evaluate_dense(kernel, x1, x2):
     """Dense kernel matrix with the reference's broadcasting: x [n,Q] | [L,n,Q] | [P,L,n,Q] against [L,1,1] parameters
-    gives [L,n1,n2] | [P,L,n1,n2]; un-batched kernels (no latent batch) give [n1,n2]."""
+    gives [L,n1,n2] | [P,L,n1,n2]; un-batched kernels (no latent batch) give [n1,n2].
+    Differentiable w.r.t. the hyper-parameters (diff_ops.KernelDense), constant in the covariates."""
+    from .diff_ops import KernelDense
     comps = flatten(kernel)
     L = latent_count(comps, default=1)
     batched = any(t is not None and (torch.is_tensor(t) or isinstance(t, Raw)) and t.numel() > 1
@@ -50,11 +53,11 @@ def evaluate_dense(kernel, x1, x2):
         P = x1.shape[0] if x1.dim() == 4 else x2.shape[0]
         f1 = x1.expand(P, L, *x1.shape[-2:]).reshape(P * L, *x1.shape[-2:])
         f2 = x2.expand(P, L, *x2.shape[-2:]).reshape(P * L, *x2.shape[-2:])
-        out = ops.kernel_dense(structure, ls, os_, f1, f2, "all")
+        out = KernelDense.apply(structure, "all", f1, f2, ls, os_, None)
         return out.view(P, L, out.shape[-2], out.shape[-1])
     a = x1 if x1.dim() < 3 or x1.shape[0] == L else x1.expand(L, *x1.shape[-2:])
     b = x2 if x2.dim() < 3 or x2.shape[0] == L else x2.expand(L, *x2.shape[-2:])
-    out = ops.kernel_dense(structure, ls, os_, a, b, "all")
+    out = KernelDense.apply(structure, "all", a, b, ls, os_, None)
     if lead == 2 and not batched:
         return out[0]
     return out

@@ -62,6 +62,55 @@ def kernel_blocks(structure, lengthscale, outputscale, x, offsets_dev, sum_T2, w
     return out
 
 
+def _comp_range(structure, which):
+    return {"k0": (0, structure.n_comp0), "k1": (structure.n_comp0, structure.n_comp), "all": (0, structure.n_comp)}[which]
+
+
+def kernel_dense_bwd(structure, lengthscale, outputscale, x1, x2, grad_out, which="all", want_diag=False):
+    """Adjoints of kernel_dense w.r.t. (lengthscale [n_ls,L], outputscale [n_comp,L], diag_add [L] | None) given the adjoint
+    of its output (lvae_kernel_dense_bwd_f64)."""
+    lib = require_cuda(x1, x2, lengthscale, outputscale, grad_out)
+    L = outputscale.shape[1]
+    lo, hi = _comp_range(structure, which)
+    x1, x2, g = _c(x1), _c(x2), _c(grad_out)
+    B = g.shape[0]
+    s1 = x1.shape[-2] * x1.shape[-1] if x1.dim() == 3 else 0
+    s2 = x2.shape[-2] * x2.shape[-1] if x2.dim() == 3 else 0
+    n1, n2, Q = x1.shape[-2], x2.shape[-2], x1.shape[-1]
+    if g.shape != (B, n1, n2) or B % L:
+        raise RuntimeError("lvae_b200: kernel_dense_bwd: adjoint shape does not match the kernel matrix")
+    ls, os_ = _c(lengthscale), _c(outputscale)
+    d_ls, d_os = torch.empty_like(ls), torch.empty_like(os_)
+    d_diag = torch.empty(L, dtype=F64, device=g.device) if want_diag else None
+    ks, keep = make_spec(structure)
+    with torch.cuda.device(g.device):
+        rc = lib.lvae_kernel_dense_bwd_f64(C.byref(ks), lo, hi, L, B, Q, ptr(x1), s1, n1, ptr(x2), s2, n2, ptr(ls), ptr(os_),
+                                           ptr(g), ptr(d_ls), ptr(d_os), ptr(d_diag), stream_ptr(g.device))
+    check(rc, "lvae_kernel_dense_bwd_f64")
+    return d_ls, d_os, d_diag
+
+
+def kernel_blocks_bwd(structure, lengthscale, outputscale, x, offsets_dev, grad_out, which="k0", want_diag=False):
+    """Adjoints of kernel_blocks (lvae_kernel_blocks_bwd_f64); grad_out flat [L, sum_T2]."""
+    lib = require_cuda(x, lengthscale, outputscale, offsets_dev, grad_out)
+    L = outputscale.shape[1]
+    lo, hi = _comp_range(structure, which)
+    x, g = _c(x), _c(grad_out)
+    P_b = offsets_dev.numel() - 1
+    if g.dim() != 2 or g.shape[0] != L:
+        raise RuntimeError("lvae_b200: kernel_blocks_bwd: adjoint must be [L, sum_T2]")
+    ls, os_ = _c(lengthscale), _c(outputscale)
+    d_ls, d_os = torch.empty_like(ls), torch.empty_like(os_)
+    d_diag = torch.empty(L, dtype=F64, device=g.device) if want_diag else None
+    ks, keep = make_spec(structure)
+    with torch.cuda.device(g.device):
+        rc = lib.lvae_kernel_blocks_bwd_f64(C.byref(ks), lo, hi, L, x.shape[1], ptr(x), ptr(offsets_dev), P_b, g.shape[1],
+                                            ptr(ls), ptr(os_), ptr(g), ptr(d_ls), ptr(d_os), ptr(d_diag),
+                                            stream_ptr(g.device))
+    check(rc, "lvae_kernel_blocks_bwd_f64")
+    return d_ls, d_os, d_diag
+
+
 def potrf_batched(A, check_info=True):
     """Lower Cholesky factors of a batch [..., n, n] (torch.cholesky, elbo_functions.py:177,179,185)."""
     lib = require_cuda(A)
