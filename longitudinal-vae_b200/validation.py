@@ -1,4 +1,5 @@
-"""Drop-in for the reference's validation.validation_dubo (validation.py:8-68), forward only, on the GPU ops."""
+"""Drop-in for the reference's validation.validation_dubo (validation.py:8-68) on the GPU ops (differentiable, see
+elbo_functions._low_rank_terms)."""
 from .elbo_functions import _dubo_per_latent
 
 
