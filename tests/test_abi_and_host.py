@@ -201,3 +201,47 @@ def test_packed_hyper_parameters_match_module_properties():
             assert (a is None) == (b is None)
             if a is not None:
                 assert torch.allclose(a, b, rtol=1e-13, atol=1e-300)
+
+
+def test_gp_model_checkpoint_round_trip(tmp_path):
+    """gp_model.pth / zt_list.pth / m.pth / H.pth (LVAE.py:213-232, 353-360): gpytorch's key layout, strict reload."""
+    from lvae_b200 import synth
+    from lvae_b200.GP_def import ExactGPModel, load_hensman_state, save_hensman_state
+    from lvae_b200.constraints import GreaterThan
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200.likelihoods import GaussianLikelihood
+    L = 3
+    b = synth.make_batch("cfg2", P=4, L=L, M=7)
+
+    def make():
+        cm0, cm1 = generate_kernel_batched(L, **b.lists, id_covariate=2)
+        lik = GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=GreaterThan(1e-8))
+        return ExactGPModel(b.x, b.mu, lik, cm0 + cm1).double(), cm0, cm1, lik
+
+    gp, cm0, cm1, lik = make()
+    keys = set(gp.state_dict().keys())
+    for k in ("likelihood.noise_covar.raw_noise", "likelihood.noise_covar.raw_noise_constraint.lower_bound",
+              "covar_module.kernels.0.raw_outputscale", "covar_module.kernels.0.base_kernel.raw_lengthscale",
+              "covar_module.kernels.0.base_kernel.raw_lengthscale_constraint.lower_bound",
+              "covar_module.kernels.0.raw_outputscale_constraint.upper_bound",
+              "covar_module.kernels.0.base_kernel.active_dims"):
+        assert k in keys, k
+    n0 = len(cm0.kernels)
+    # the sum shares the parameters of its two operands (LVAE.py:196): same storage under both names
+    assert gp.covar_module.kernels[n0].raw_outputscale is cm1.kernels[0].raw_outputscale
+    with torch.no_grad():
+        for p in gp.parameters():
+            p.add_(torch.randn_like(p))
+    save_hensman_state(str(tmp_path), gp, b.z, b.m, b.H)
+    save_hensman_state(str(tmp_path), gp, b.z, b.m, b.H, suffix="_best")
+    gp2, cm0b, cm1b, lik2 = make()
+    z2, m2, H2 = load_hensman_state(str(tmp_path), gp2, "cpu")
+    for (k, a), (k2, c) in zip(gp.state_dict().items(), gp2.state_dict().items()):
+        assert k == k2 and torch.equal(a, c)
+    assert torch.equal(z2, b.z) and torch.equal(m2, b.m) and torch.equal(H2, b.H)
+    assert torch.equal(lik2.noise, lik.noise) and torch.equal(cm1b.kernels[0].outputscale, cm1.kernels[0].outputscale)
+    # a checkpoint with a missing key is rejected (strict), as with gpytorch
+    sd = gp.state_dict()
+    sd.pop("covar_module.kernels.0.raw_outputscale")
+    with pytest.raises(RuntimeError):
+        gp2.load_state_dict(sd)
