@@ -252,7 +252,7 @@ int lvae_potrf_big_abi(double* A, int n, int64_t stride, int batch, int32_t* inf
     const int np = lvae_pad_order(n), nb = np >> 6;
     double* buf = nullptr;
     const size_t doubles = (size_t)batch * np * np + (size_t)batch * nb * 4096;
-    cudaError_t e = cudaMallocAsync((void**)&buf, sizeof(double) * doubles, st);
+    cudaError_t e = lvae_scratch_alloc((void**)&buf, sizeof(double) * doubles, st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
     double* F = buf;
     double* dinv = F + (size_t)batch * np * np;
@@ -267,7 +267,7 @@ int lvae_potri_big_abi(const double* Lc, double* Ainv, int n, int64_t stride, in
     const int np = lvae_pad_order(n), nb = np >> 6;
     double* buf = nullptr;
     const size_t ms = (size_t)batch * np * np;
-    cudaError_t e = cudaMallocAsync((void**)&buf, sizeof(double) * (3 * ms + (size_t)batch * nb * 4096), st);
+    cudaError_t e = lvae_scratch_alloc((void**)&buf, sizeof(double) * (3 * ms + (size_t)batch * nb * 4096), st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
     double* F = buf;
     double* X = F + ms;

@@ -11,6 +11,22 @@ int64_t& lvae_launch_counter() {
     return c;
 }
 
+cudaError_t lvae_scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static bool tuned[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !tuned[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = 2ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 8, st);
+}
+
 int lvae_make_devspec(const lvae_kernel_spec_t* ks, int Q, DevSpec* out) {
     if (!ks || !ks->spec) return LVAE_E_BADARG;
     const int nc = ks->n_comp0 + ks->n_comp1;
@@ -148,7 +164,7 @@ extern "C" int lvae_kernel_blocks_f64(const lvae_kernel_spec_t* ks, int32_t comp
     if (P_b == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int64_t* off2 = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&off2, sizeof(int64_t) * ((size_t)P_b + 1), st);
+    cudaError_t e = lvae_scratch_alloc((void**)&off2, sizeof(int64_t) * ((size_t)P_b + 1), st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
     rc = lvae_block_offsets(offsets, P_b, off2, st);
     if (!rc) {
@@ -195,7 +211,7 @@ extern "C" int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n,
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 64) return lvae_potri_big_abi(Lc, Ainv, n, batch_stride, batch, st);
     double* tmp = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&tmp, sizeof(double) * (size_t)batch * n * n, st);
+    cudaError_t e = lvae_scratch_alloc((void**)&tmp, sizeof(double) * (size_t)batch * n * n, st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
     k_potri<<<batch, 256, 0, st>>>(Lc, Ainv, tmp, n, batch_stride);
     LVAE_COUNT_LAUNCH();

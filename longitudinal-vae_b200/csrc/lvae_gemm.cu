@@ -173,18 +173,68 @@ int lvae_gemm(const GemmDesc& din, cudaStream_t st) {
     return d.tb ? launch<false, true>(d, al16, st) : launch<false, false>(d, al16, st);
 }
 
-// C ABI (include/lvae_b200.h): one batch dimension, no split-K.
+// C[b][i][j] = alpha * sum_s part[s][b][i][j] + beta * C[b][i][j]; fixed summation order.  lower_only: entries j > i untouched.
+__global__ void __launch_bounds__(256) k_splitk_reduce(const double* __restrict__ part, int ksplit, int64_t per_split,
+                                                       int m, int n, double alpha, double beta, double* __restrict__ C,
+                                                       int ldc, int64_t sC, int64_t total, int lower_only) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / ((int64_t)m * n), r = e - b * (int64_t)m * n;
+        const int i = (int)(r / n), j = (int)(r - (int64_t)i * n);
+        if (lower_only && j > i) continue;
+        double a = 0.0;
+        for (int s = 0; s < ksplit; ++s) a += part[(size_t)s * per_split + e];
+        double* c = C + (size_t)b * sC + (size_t)i * ldc + j;
+        *c = beta == 0.0 ? alpha * a : fma(alpha, a, beta * *c);
+    }
+}
+
+// C ABI (include/lvae_b200.h): one batch dimension.  A product with few output tiles and a long k (S = Kxz^T B^-1 Kxz over
+// all rows of a data set: 60 x 60 x 20 000) would leave most of the 148 SMs idle, so the k range is split over ~2 waves of
+// CTAs into a scratch buffer and summed in a fixed order.
 extern "C" int lvae_gemm_batched_f64(int32_t trans_a, int32_t trans_b, int32_t m, int32_t n, int32_t k, double alpha,
                                      const double* A, int32_t lda, int64_t stride_a, const double* B, int32_t ldb,
                                      int64_t stride_b, double beta, double* C, int32_t ldc, int64_t stride_c,
                                      int32_t batch, int32_t flags, void* stream) {
     if (m < 0 || n < 0 || k < 0 || batch < 0 || !A || !B || !C) return LVAE_E_BADARG;
     if ((flags & LVAE_GEMM_MIRROR) && beta != 0.0) return LVAE_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
     GemmDesc d;
     d.A = A; d.B = B; d.C = C;
     d.m = m; d.n = n; d.k = k; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
     d.ta = trans_a; d.tb = trans_b;
     d.batch = batch; d.sA = stride_a; d.sB = stride_b; d.sC = stride_c;
     d.alpha = alpha; d.beta = beta; d.flags = flags;
-    return lvae_gemm(d, (cudaStream_t)stream);
+    const int64_t ctas = (int64_t)((m + BM - 1) / BM) * ((n + BN - 1) / BN) * batch;
+    int ksplit = 1;
+    if (ctas > 0 && ctas < 148 && k >= 2048) {
+        int64_t want = (2 * 148 + ctas - 1) / ctas;
+        if (want > k / 512) want = k / 512;
+        if (want * batch > 65535) want = 65535 / batch;
+        ksplit = (int)want;
+    }
+    if (ksplit <= 1) return lvae_gemm(d, st);
+    int kchunk = (k + ksplit - 1) / ksplit;
+    kchunk = (kchunk + BK - 1) / BK * BK;
+    ksplit = (k + kchunk - 1) / kchunk;
+    const int64_t per_split = (int64_t)batch * m * n;
+    double* part = nullptr;
+    cudaError_t e = lvae_scratch_alloc((void**)&part, sizeof(double) * (size_t)per_split * ksplit, st);
+    if (e != cudaSuccess) return lvae_cuda_rc(e);
+    d.C = part; d.ldc = n; d.sC = (int64_t)m * n;
+    d.ksplit = ksplit; d.kchunk = kchunk;
+    d.kA = trans_a ? (int64_t)kchunk * lda : kchunk;
+    d.kB = trans_b ? kchunk : (int64_t)kchunk * ldb;
+    d.kC = per_split;
+    d.alpha = 1.0; d.beta = 0.0;
+    int rc = lvae_gemm(d, st);
+    if (!rc) {
+        const int lower_only = (flags & LVAE_GEMM_LOWER) && !(flags & LVAE_GEMM_MIRROR);
+        const int blocks = (int)((per_split + 255) / 256 < 148 * 8 ? (per_split + 255) / 256 : 148 * 8);
+        k_splitk_reduce<<<blocks, 256, 0, st>>>(part, ksplit, per_split, m, n, alpha, beta, C, ldc, stride_c, per_split,
+                                                lower_only);
+        LVAE_COUNT_LAUNCH();
+        rc = lvae_cuda_rc(cudaGetLastError());
+    }
+    cudaFreeAsync(part, st);
+    return rc;
 }

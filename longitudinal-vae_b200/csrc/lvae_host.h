@@ -8,6 +8,11 @@
 static inline int lvae_cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
 int lvae_make_devspec(const lvae_kernel_spec_t* ks, int Q, DevSpec* out);
 int lvae_block_offsets(const int32_t* offsets, int P_b, int64_t* off2, cudaStream_t st);
+// Stream-ordered scratch for the stand-alone ABI entry points (cudaMallocAsync from the device's default pool).  On first
+// use per device the pool's release threshold is raised to 2 GiB: with the default of 0 every synchronisation (e.g. the
+// Cholesky info check) hands the scratch back to the driver and the next call pays a fresh allocation — milliseconds for
+// the 100 MB a batched inverse of 32 000 blocks needs.  Free with cudaFreeAsync.
+cudaError_t lvae_scratch_alloc(void** p, size_t bytes, cudaStream_t st);
 
 // optional per-phase device timing (bench.py's roofline: duration of the dominant kernel measured live with CUDA events
 // on the launch stream).  Phases: 0 head, 1 prep, 2 subjects, 3 reduce, 4 tail, 5 ng_step.

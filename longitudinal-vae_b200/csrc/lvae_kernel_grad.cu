@@ -164,7 +164,7 @@ extern "C" int lvae_kernel_dense_bwd_f64(const lvae_kernel_spec_t* ks, int32_t c
     const int n_rep = n_batch / L;
     const int n_chunk = grad_chunks((int64_t)n1 * n2 * n_rep, L);
     double* part = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&part, sizeof(double) * (size_t)L * n_chunk * GRAD_ROW, st);
+    cudaError_t e = lvae_scratch_alloc((void**)&part, sizeof(double) * (size_t)L * n_chunk * GRAD_ROW, st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
     k_dense_bwd<<<dim3(n_chunk, L), GRAD_THREADS, 0, st>>>(sp, comp_begin, comp_end, Q, x1, s1, n1, x2, s2, n2, lengthscale, L,
                                                            n_rep, grad_out, d_diag_add != nullptr, part);
@@ -191,9 +191,9 @@ extern "C" int lvae_kernel_blocks_bwd_f64(const lvae_kernel_spec_t* ks, int32_t 
     if (n_chunk > P_b) n_chunk = P_b > 0 ? P_b : 1;
     int64_t* off2 = nullptr;
     double* part = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&off2, sizeof(int64_t) * ((size_t)P_b + 1), st);
+    cudaError_t e = lvae_scratch_alloc((void**)&off2, sizeof(int64_t) * ((size_t)P_b + 1), st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
-    e = cudaMallocAsync((void**)&part, sizeof(double) * (size_t)L * n_chunk * GRAD_ROW, st);
+    e = lvae_scratch_alloc((void**)&part, sizeof(double) * (size_t)L * n_chunk * GRAD_ROW, st);
     if (e != cudaSuccess) { cudaFreeAsync(off2, st); return lvae_cuda_rc(e); }
     rc = lvae_block_offsets(offsets, P_b, off2, st);
     if (!rc) {

@@ -21,12 +21,13 @@ def _dense(structure, ls, os_, x1, x2, which, diag):
     a = x1.to(F64) if x1.dim() == 3 else x1.to(F64).unsqueeze(0).expand(B, -1, -1)
     b = x2.to(F64) if x2.dim() == 3 else x2.to(F64).unsqueeze(0).expand(B, -1, -1)
     n1, n2 = a.shape[1], b.shape[1]
-    lat = torch.arange(B) % L
-    out = torch.zeros(B, n1, n2, dtype=F64)
+    dev = a.device
+    lat = torch.arange(B, device=dev) % L
+    out = torch.zeros(B, n1, n2, dtype=F64, device=dev)
     lo, hi = _rng(structure, which)
     for c in range(lo, hi):
         row = [int(v) for v in structure.table[c]]
-        f = torch.ones(B, n1, n2, dtype=F64)
+        f = torch.ones(B, n1, n2, dtype=F64, device=dev)
         for i in range(row[2]):
             ty, dm = row[3 + 2 * i], row[4 + 2 * i]
             u, v = a[:, :, dm].unsqueeze(2), b[:, :, dm].unsqueeze(1)
@@ -37,7 +38,7 @@ def _dense(structure, ls, os_, x1, x2, which, diag):
             f = f * torch.exp(-d * d / (2 * ell * ell))
         out = out + os_[c][lat].view(B, 1, 1) * f
     if diag is not None:
-        out = out + diag[lat].view(B, 1, 1) * torch.eye(n1, n2, dtype=F64)
+        out = out + diag[lat].view(B, 1, 1) * torch.eye(n1, n2, dtype=F64, device=dev)
     return out
 
 
@@ -48,6 +49,11 @@ def kernel_dense(structure, lengthscale, outputscale, x1, x2, which="all", diag_
 
 def _blocks(structure, ls, os_, x, offsets, which, diag):
     off = offsets.tolist()
+    L, P = os_.shape[1], len(off) - 1
+    T = off[1] - off[0] if P else 0
+    if P and all(off[p + 1] - off[p] == T for p in range(P)):         # equal T: one stacked evaluation, matrix p*L + l
+        xs = x.reshape(P, 1, T, -1).expand(P, L, T, x.shape[-1]).reshape(P * L, T, -1)
+        return _dense(structure, ls, os_, xs, xs, which, diag).view(P, L, T * T).permute(1, 0, 2).reshape(L, P * T * T)
     parts = []
     for p in range(len(off) - 1):
         xp = x[off[p]:off[p + 1]]
@@ -65,7 +71,7 @@ def kernel_blocks(structure, lengthscale, outputscale, x, offsets_dev, sum_T2, w
 def _bwd(fn, ls, os_, diag, g):
     ls = ls.detach().clone().requires_grad_(True)
     os_ = os_.detach().clone().requires_grad_(True)
-    dg = torch.zeros(os_.shape[1], dtype=F64, requires_grad=True) if diag else None
+    dg = torch.zeros(os_.shape[1], dtype=F64, device=os_.device, requires_grad=True) if diag else None
     with torch.enable_grad():
         out = fn(ls, os_, dg)
         grads = torch.autograd.grad(out, [ls, os_] + ([dg] if diag else []), g, allow_unused=True)

@@ -14,7 +14,9 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
-@pytest.mark.parametrize("m,n,k", [(128, 64, 16), (200, 72, 61), (7, 5, 3), (256, 256, 256), (130, 190, 1000)])
+# the last three have few output tiles and a long k: the ABI entry splits the k range over CTAs and sums the parts
+@pytest.mark.parametrize("m,n,k", [(128, 64, 16), (200, 72, 61), (7, 5, 3), (256, 256, 256), (130, 190, 1000),
+                                   (60, 1, 20000), (60, 60, 20001), (7, 5, 5000)])
 def test_gemm_matches_torch(ta, tb, m, n, k):
     torch.manual_seed(m * 7 + n * 3 + k)
     batch = 3
@@ -26,7 +28,7 @@ def test_gemm_matches_torch(ta, tb, m, n, k):
     assert rel(out, ref) < 1e-12
 
 
-@pytest.mark.parametrize("n,k", [(72, 500), (128, 33), (256, 2000)])
+@pytest.mark.parametrize("n,k", [(72, 500), (128, 33), (256, 2000), (60, 20000), (256, 4100)])
 def test_gemm_syrk_lower_mirror(n, k):
     torch.manual_seed(n + k)
     U = torch.randn(2, k, n, dtype=torch.float64, device="cuda")
