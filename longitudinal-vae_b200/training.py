@@ -51,7 +51,7 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
     curves = {k: [] for k in ("net", "recon", "nll", "kld", "penalty")}
     best_epoch = 0
     for epoch in range(1, epochs + 1):
-        sums = dict(net=0.0, recon=0.0, nll=0.0, kld=0.0)
+        acc = None                                             # running [net, recon, nll, kld] / n_batches, kept on the device
         for sample_batched in dataloader:
             optimiser.zero_grad()
             nnet_model.train()
@@ -88,9 +88,9 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
             if natural_gradient:                                                                 # 129-135
                 m, H = natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr)
             vals = torch.stack([net_loss.detach().sum(), recon_loss.detach(), nll_loss.detach(),
-                                kld_loss.detach().sum()]).tolist()                               # one sync instead of four (137-140)
-            for k, v in zip(("net", "recon", "nll", "kld"), vals):
-                sums[k] += v / n_batches
+                                kld_loss.detach().sum()]).double() / n_batches                   # 137-140 without the four
+            acc = vals if acc is None else acc + vals                                            # .item() syncs per step
+        sums = dict(zip(("net", "recon", "nll", "kld"), acc.tolist()))                           # one sync per epoch
         if verbose:
             print('Iter %d/%d - Loss: %.3f  - GP loss: %.3f  - NLL Loss: %.3f  - Recon Loss: %.3f' % (
                 epoch, epochs, sums["net"], sums["kld"], sums["nll"], sums["recon"]), flush=True)
