@@ -519,6 +519,32 @@ def main():
             EF.set_error_check("immediate")
         except Exception as ex:
             lat["e2e_unavailable"] = repr(ex)[:160]
+        if not ragged:
+            try:  # public API again, but the GP side of the step is ONE graph replay (lvae_b200.graphed.GraphedHensmanStep)
+                from lvae_b200.graphed import GraphedHensmanStep
+                mg, Hg = m0.clone().reshape(L, M, 1).contiguous(), H0.clone().contiguous()
+                gstep = GraphedHensmanStep(cm0, cm1, lik, L, mg, Hg, z, P_tot, spb2, int(b.T), 1e-6, lr)
+
+                def small_graphed():
+                    xd = hx2.to(device, non_blocking=True)
+                    mud = hmu2.to(device, non_blocking=True).requires_grad_(True)
+                    lvd = hlv2.to(device, non_blocking=True).requires_grad_(True)
+                    gstep(xd, mud, lvd).backward()
+                    o_mu.copy_(mud.grad, non_blocking=True)
+                    cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True)
+                for _ in range(5):
+                    small_graphed()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    small_graphed()
+                torch.cuda.synchronize()
+                lat["graphed_api_ms_per_step"] = (time.perf_counter() - t0) / 50 * 1e3
+                lat["graphed_api_subjects_per_s"] = spb2 / (lat["graphed_api_ms_per_step"] * 1e-3)
+                gstep.check_errors()
+                lat["graphed_api_finite"] = bool(torch.isfinite(Hg).all())
+            except Exception as ex:
+                lat["graphed_api_unavailable"] = repr(ex)[:200]
         try:      # the same step captured once into a CUDA graph (the C ABI is stream-ordered and capture-safe) and replayed
             side = torch.cuda.Stream(device)
             side.wait_stream(torch.cuda.current_stream(device))
