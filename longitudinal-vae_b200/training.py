@@ -33,9 +33,12 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
                      natural_gradient=False, natural_gradient_lr=0.01, subjects_per_batch=20, memory_dbg=False,
                      eps=1e-6, results_path=None, validation_dataset=None, generation_dataset=None,
                      prediction_dataset=None, gp_model=None, csv_file_test_data=None, csv_file_test_label=None,
-                     test_mask_file=None, data_source_path=None, num_workers=4, on_validation=None, verbose=True):
+                     test_mask_file=None, data_source_path=None, num_workers=4, on_validation=None, verbose=True,
+                     cuda_graph=False):
     """Minibatch SVI training [Hensman et al. 2013] of the L-VAE (training.py:15-237).  Returns
-    (penalty_term_arr, net_train_loss_arr, nll_loss_arr, recon_loss_arr, kld_loss_arr, m, H, best_epoch)."""
+    (penalty_term_arr, net_train_loss_arr, nll_loss_arr, recon_loss_arr, kld_loss_arr, m, H, best_epoch).
+    cuda_graph=True (fixed T, natural-gradient mode): full minibatches run the GP side of the step as one CUDA-graph replay
+    (graphed.GraphedHensmanStep); the last, shorter minibatch of an epoch takes the ordinary calls."""
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
     N = len(dataset)
     assert type_KL == 'GPapprox_closed'
@@ -47,6 +50,16 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
         n_batches = (P * T + batch_size - 1) // batch_size
         sampler = BatchSampler(SubjectSampler(dataset, P, T), batch_size, drop_last=False)
     dataloader = HensmanDataLoader(dataset, batch_sampler=sampler, num_workers=num_workers)
+
+    gstep = None
+    if cuda_graph:
+        if varying_T or not natural_gradient:
+            raise ValueError("lvae_b200: cuda_graph=True needs fixed T and natural_gradient=True")
+        from .graphed import GraphedHensmanStep
+        m = m.detach().to(torch.float64).contiguous().clone()              # updated in place from here on
+        H = H.detach().to(torch.float64).contiguous().clone()
+        gstep = GraphedHensmanStep(covar_module0, covar_module1, likelihoods, latent_dim, m, H, zt_list, P,
+                                   subjects_per_batch, T, eps, natural_gradient_lr)
 
     curves = {k: [] for k in ("net", "recon", "nll", "kld", "penalty")}
     best_epoch = 0
@@ -66,7 +79,11 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
             recon_loss, nll = nnet_model.loss_function(recon_batch, data, mask)
             recon_loss, nll_loss = torch.sum(recon_loss), torch.sum(nll)
             PSD_H = H if natural_gradient else torch.matmul(H, H.transpose(-1, -2))              # 108
-            if varying_T:                                                                        # 110-115
+            graphed = gstep is not None and N_batch == subjects_per_batch * T
+            if graphed:                                       # bound, all gradients and the update of (m, H): one replay
+                P_in_current_batch = subjects_per_batch
+                kld_loss = gstep(train_x, mu, log_var)
+            elif varying_T:                                                                      # 110-115
                 P_in_current_batch = torch.unique(train_x[:, id_covariate]).shape[0]
                 kld_loss, grad_m, grad_H = minibatch_KLD_upper_bound_iter(
                     covar_module0, covar_module1, likelihoods, latent_dim, m, PSD_H, train_x, mu, log_var, zt_list, P,
@@ -85,8 +102,13 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
                 net_loss = recon_loss + weight * kld_loss
             net_loss.sum().backward()                                                            # 126-127
             optimiser.step()
-            if natural_gradient:                                                                 # 129-135
-                m, H = natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr)
+            if natural_gradient and not graphed:                                                 # 129-135
+                m2, H2 = natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr)
+                if gstep is not None:                         # keep the tensors the graph is bound to
+                    m.copy_(m2.view_as(m))
+                    H.copy_(H2)
+                else:
+                    m, H = m2, H2
             vals = torch.stack([net_loss.detach().sum(), recon_loss.detach(), nll_loss.detach(),
                                 kld_loss.detach().sum()]).double() / n_batches                   # 137-140 without the four
             acc = vals if acc is None else acc + vals                                            # .item() syncs per step
@@ -101,5 +123,7 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
             if on_validation(epoch, dict(nnet_model=nnet_model, covar_module0=covar_module0, covar_module1=covar_module1,
                                          likelihoods=likelihoods, zt_list=zt_list, m=m, H=H)):
                 best_epoch = epoch
+    if gstep is not None:
+        gstep.check_errors()
     arr = lambda k: np.asarray(curves[k], dtype=np.float64)
     return arr("penalty"), arr("net"), arr("nll"), arr("recon"), arr("kld"), m, H, best_epoch

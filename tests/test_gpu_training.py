@@ -78,7 +78,8 @@ def _oracle_loop(model, ds, k0, k1, noise, L, m, H, z, P, T, spb, epochs, weight
     return np.array(kld_curve), m, H
 
 
-def test_hensman_training_matches_oracle_loop():
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_hensman_training_matches_oracle_loop(cuda_graph):
     import copy
     import lvae_oracle as orc
     from helpers import build_modules, rel
@@ -109,7 +110,7 @@ def test_hensman_training_matches_oracle_loop():
     np.random.seed(42)
     out = hensman_training(model_gpu, 'conv', epochs, ds, opt, 'GPapprox_closed', 1, L, cm0, cm1, lik, b.m.cuda(), b.H.cuda(),
                            b.z.cuda(), P, T, False, 6, 0.15, 2, 'mse', natural_gradient=True, natural_gradient_lr=0.01,
-                           subjects_per_batch=spb, num_workers=0, verbose=False)
+                           subjects_per_batch=spb, num_workers=0, verbose=False, cuda_graph=cuda_graph)
     # identical batches, initial weights and optimiser state on both sides: the per-epoch GP loss and the final (m, H) agree
     assert out[4].shape == (epochs,)
     assert np.abs(out[4] - ref_curve).max() <= 1e-6 * np.abs(ref_curve).max()
