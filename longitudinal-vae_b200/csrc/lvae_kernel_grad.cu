@@ -5,7 +5,8 @@
 //     d/d diag_add[l]       = sum_i G_ii
 // per latent.  These make the non-minibatch bounds (deviance_upper_bound / elbo, elbo_functions.py:36-142) trainable
 // through autograd the way gpytorch's lazy kernels are in the reference; the Hensman step has its own fused adjoints
-// (lvae_subjects_fused*.cu) and never comes here.  Read-bound: 8 bytes of G per entry and component, covariates from L1.
+// (lvae_subjects_fused*.cu) and never comes here.  Per entry and component: one exp (the table-driven one of
+// lvae_common.cuh) and 8 bytes of G (re-read per component, rolled component loop); covariates come from L1.
 // Two launches, no atomics: per-CTA partial rows, then a fixed-order sum per latent (bitwise reproducible).
 #include "lvae_host.h"
 
@@ -25,30 +26,35 @@ __device__ __forceinline__ void grad_setup(GradSetup& s, const DevSpec& sp, cons
     __syncthreads();
 }
 
-// matrix b of the batch uses latent b % L; grid (n_chunk, L): CTA (ch, l) walks the entries of latent l's matrices
+// matrix b of the batch uses latent b % L; grid (ceil(n2/64), n_chunk, L), 256 threads as 64 columns x 4 rows (the layout
+// of the forward kernel: coalesced on j, no integer division per entry); CTA (cx, ch, l) walks rows ch*4+ty, +4*n_chunk, ...
 __global__ void __launch_bounds__(GRAD_THREADS) k_dense_bwd(DevSpec sp, int c0, int c1, int Q, const double* __restrict__ x1,
                                                             int64_t s1, int n1, const double* __restrict__ x2, int64_t s2,
                                                             int n2, const double* __restrict__ ls, int L, int n_rep,
                                                             const double* __restrict__ G, int want_diag,
                                                             double* __restrict__ part) {
     __shared__ GradSetup s;
-    const int l = blockIdx.y;
+    const int l = blockIdx.z;
     grad_setup(s, sp, ls, L, l);
-    const int64_t per = (int64_t)n1 * n2, total = per * n_rep;
-    const int64_t step = (int64_t)gridDim.x * GRAD_THREADS, e0 = (int64_t)blockIdx.x * GRAD_THREADS + threadIdx.x;
-    double* row = part + ((size_t)l * gridDim.x + blockIdx.x) * GRAD_ROW;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int j = blockIdx.x * 64 + tx, istep = 4 * gridDim.y;
+    const int64_t per = (int64_t)n1 * n2;
+    double* row = part + ((size_t)l * gridDim.y * gridDim.x + (size_t)blockIdx.y * gridDim.x + blockIdx.x) * GRAD_ROW;
     for (int c = c0; c < c1; ++c) {
         double a = 0.0, a2 = 0.0;
-        for (int64_t e = e0; e < total; e += step) {
-            const int rep = (int)(e / per);
-            const int64_t r = e - (int64_t)rep * per;
-            const int i = (int)(r / n2), j = (int)(r - (int64_t)i * n2);
-            const int64_t b = (int64_t)rep * L + l;
-            double d2;
-            const double f = comp_value(sp, c, x1 + b * s1 + (size_t)i * Q, x2 + b * s2 + (size_t)j * Q, s.hil2, d2, s.etab);
-            const double gf = G[b * per + r] * f;
-            a += gf;
-            a2 = fma(gf, d2, a2);
+        if (j < n2) {
+            for (int rep = 0; rep < n_rep; ++rep) {
+                const int64_t b = (int64_t)rep * L + l;
+                const double* xb = x2 + b * s2 + (size_t)j * Q;
+                const double* g = G + b * per + j;
+                for (int i = blockIdx.y * 4 + ty; i < n1; i += istep) {
+                    double d2;
+                    const double f = comp_value(sp, c, x1 + b * s1 + (size_t)i * Q, xb, s.hil2, d2, s.etab);
+                    const double gf = g[(size_t)i * n2] * f;
+                    a += gf;
+                    a2 = fma(gf, d2, a2);
+                }
+            }
         }
         a = block_sum(a, s.red);
         a2 = block_sum(a2, s.red);
@@ -56,11 +62,10 @@ __global__ void __launch_bounds__(GRAD_THREADS) k_dense_bwd(DevSpec sp, int c0, 
     }
     double dg = 0.0;
     if (want_diag) {
-        const int nd = min(n1, n2);
-        for (int64_t e = e0; e < (int64_t)nd * n_rep; e += step) {
-            const int rep = (int)(e / nd), i = (int)(e - (int64_t)rep * nd);
-            dg += G[((int64_t)rep * L + l) * per + (int64_t)i * n2 + i];
-        }
+        if (j < n2 && j < n1)
+            for (int rep = 0; rep < n_rep; ++rep)
+                for (int i = blockIdx.y * 4 + ty; i < n1; i += istep)
+                    if (i == j) dg += G[((int64_t)rep * L + l) * per + (int64_t)i * n2 + i];
         dg = block_sum(dg, s.red);
     }
     if (threadIdx.x == 0) row[2 * LVAE_MAXC] = dg;
@@ -162,12 +167,17 @@ extern "C" int lvae_kernel_dense_bwd_f64(const lvae_kernel_spec_t* ks, int32_t c
         return LVAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_rep = n_batch / L;
-    const int n_chunk = grad_chunks((int64_t)n1 * n2 * n_rep, L);
+    const int ncx = n2 > 0 ? (n2 + 63) / 64 : 1;
+    int ncy = grad_chunks((int64_t)n1 * n2 * n_rep, L) / ncx;          // row chunks per column block
+    if (ncy > (n1 + 3) / 4) ncy = (n1 + 3) / 4;
+    if (ncy < 1) ncy = 1;
+    if (ncy > 65535 || ncx > 65535) return LVAE_E_TOO_LARGE;
+    const int n_chunk = ncx * ncy;
     double* part = nullptr;
     cudaError_t e = lvae_scratch_alloc((void**)&part, sizeof(double) * (size_t)L * n_chunk * GRAD_ROW, st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);
-    k_dense_bwd<<<dim3(n_chunk, L), GRAD_THREADS, 0, st>>>(sp, comp_begin, comp_end, Q, x1, s1, n1, x2, s2, n2, lengthscale, L,
-                                                           n_rep, grad_out, d_diag_add != nullptr, part);
+    k_dense_bwd<<<dim3(ncx, ncy, L), GRAD_THREADS, 0, st>>>(sp, comp_begin, comp_end, Q, x1, s1, n1, x2, s2, n2, lengthscale, L,
+                                                            n_rep, grad_out, d_diag_add != nullptr, part);
     LVAE_COUNT_LAUNCH();
     rc = lvae_cuda_rc(cudaGetLastError());
     if (!rc) rc = grad_finish(sp, comp_begin, comp_end, n_chunk, part, lengthscale, outputscale, L, d_lengthscale,

@@ -5,7 +5,7 @@ python -m pytest tests -m gpu -q 2>&1 | tail -4
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py > gpurun_out/bench_check_cfg2.json 2> gpurun_out/bench_check_cfg2.err
 for c in "cfg3 1000" "cfg4 2000" "cfg5 2000"; do set -- $c
-python bench.py --cfg $1 --spb $2 --steps 3 --warmup 3 --no-cpu-baseline --no-latency-point > gpurun_out/bench_check_$1.json 2> gpurun_out/bench_check_$1.err
+python bench.py --cfg $1 --spb $2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_check_$1.json 2> gpurun_out/bench_check_$1.err
 done
 python - <<'PY'
 import json
