@@ -53,8 +53,8 @@ def test_dense_kernels_and_masks(name):
     assert rel(cm0(z, z).evaluate(), g["K0zz"]) < 1e-12
     for p in range(2):
         xs = x[int(g["offsets"][p]):int(g["offsets"][p + 1])].unsqueeze(0).expand(L, -1, -1)
-        k0 = cm0(xs, xs).evaluate().cpu().numpy()
-        k1 = cm1(xs, xs).evaluate().cpu().numpy()
+        k0 = cm0(xs, xs).evaluate().detach().cpu().numpy()      # a graph node, as with gpytorch
+        k1 = cm1(xs, xs).evaluate().detach().cpu().numpy()
         assert rel(k0, g[f"K0_block{p}"]) < 1e-12 and rel(k1, g[f"K1_block{p}"]) < 1e-12
         # categorical / binary structure: identical zero pattern (exact float equality tests, as the reference)
         assert np.array_equal(k0 == 0, g[f"K0_block{p}"] == 0) and np.array_equal(k1 == 0, g[f"K1_block{p}"] == 0)
