@@ -194,11 +194,91 @@ __global__ void __launch_bounds__(256) k_potri(const double* __restrict__ Lc, do
     cta_gram_lower(X, Ainv + (size_t)blockIdx.x * stride, n, n);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// n <= 32 (the per-subject T x T blocks of deviance_upper_bound / elbo / batch_predict, thousands per call): one WARP per
+// matrix in shared memory instead of one 256-thread CTA per matrix in global memory.  Lane i owns row i of the factor;
+// odd row stride -> conflict-free column walks.  Same operation order per entry as cta_cholesky.
+// ---------------------------------------------------------------------------------------------------------------
+#define SMALL_WARPS 4
+__global__ void __launch_bounds__(32 * SMALL_WARPS) k_potrf_warp(double* __restrict__ A, int n, int64_t stride, int batch,
+                                                                 int32_t* info) {
+    extern __shared__ double sm_small[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, ld = n | 1;
+    const int64_t b = (int64_t)blockIdx.x * SMALL_WARPS + w;
+    if (b >= batch) return;
+    double* S = sm_small + (size_t)w * n * ld;
+    double* Ab = A + b * stride;
+    for (int i = 0; i < n; ++i)
+        if (lane < n) S[i * ld + lane] = Ab[(size_t)i * n + lane];
+    __syncwarp();
+    int fail = 0;
+    for (int k = 0; k < n; ++k) {
+        double d = S[k * ld + k];
+        if (!(d > 0.0)) { if (!fail) fail = k + 1; d = nan(""); }
+        else d = sqrt(d);
+        __syncwarp();
+        if (lane == k) S[k * ld + k] = d;
+        const double inv = 1.0 / d;
+        const bool below = lane > k && lane < n;
+        double lik = 0.0;
+        if (below) { lik = S[lane * ld + k] * inv; S[lane * ld + k] = lik; }
+        __syncwarp();
+        if (below)
+            for (int j = k + 1; j <= lane; ++j) S[lane * ld + j] -= lik * S[j * ld + k];
+        __syncwarp();
+    }
+    for (int i = 0; i < n; ++i)
+        if (lane < n) Ab[(size_t)i * n + lane] = lane <= i ? S[i * ld + lane] : 0.0;
+    if (fail && lane == 0) atomicCAS(info, 0, (int)b + 1);
+}
+
+// Ainv = L^-T L^-1 from the lower factor: lane c solves L x = e_c (column c of X = L^-1), then lane b forms column b of X^T X.
+__global__ void __launch_bounds__(32 * SMALL_WARPS) k_potri_warp(const double* __restrict__ Lc, double* __restrict__ Ainv,
+                                                                 int n, int64_t stride, int batch) {
+    extern __shared__ double sm_small[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, ld = n | 1;
+    const int64_t b = (int64_t)blockIdx.x * SMALL_WARPS + w;
+    if (b >= batch) return;
+    double* S = sm_small + (size_t)w * 2 * n * ld;
+    double* X = S + (size_t)n * ld;
+    const double* Lb = Lc + b * stride;
+    for (int i = 0; i < n; ++i)
+        if (lane < n) S[i * ld + lane] = Lb[(size_t)i * n + lane];
+    __syncwarp();
+    if (lane < n) {
+        for (int i = 0; i < n; ++i) {                      // uniform trip counts; the predicate k >= lane selects the terms
+            double s = 0.0;
+            for (int k = 0; k < i; ++k) {
+                const double lik = S[i * ld + k];          // broadcast
+                if (k >= lane) s = fma(lik, X[k * ld + lane], s);
+            }
+            const double dii = S[i * ld + i];
+            X[i * ld + lane] = i < lane ? 0.0 : (i == lane ? 1.0 / dii : -s / dii);
+        }
+    }
+    __syncwarp();
+    double* Ob = Ainv + b * stride;
+    if (lane < n) {
+        for (int a = 0; a < n; ++a) {
+            double s = 0.0;
+            for (int i = a; i < n; ++i) s = fma(X[i * ld + a], X[i * ld + lane], s);     // X[i][lane] = 0 for i < lane
+            Ob[(size_t)a * n + lane] = s;
+        }
+    }
+}
+
 extern "C" int lvae_potrf_batched_f64(double* A, int32_t n, int64_t batch_stride, int32_t batch, int32_t* info,
                                       void* stream) {
     if (n <= 0 || n > LVAE_MAX_M || batch < 0 || batch_stride < (int64_t)n * n) return LVAE_E_BADARG;
     if (batch == 0) return 0;
     if (n > 64) return lvae_potrf_big_abi(A, n, batch_stride, batch, info, (cudaStream_t)stream);
+    if (n <= 32 && batch >= 64) {
+        const size_t smem = sizeof(double) * SMALL_WARPS * n * (n | 1);
+        k_potrf_warp<<<(batch + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, smem, (cudaStream_t)stream>>>(
+            A, n, batch_stride, batch, info);
+        LVAE_COUNT_LAUNCH();
+        return lvae_cuda_rc(cudaGetLastError());
+    }
     k_potrf<<<batch, 256, 0, (cudaStream_t)stream>>>(A, n, batch_stride, info);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());
@@ -210,6 +290,19 @@ extern "C" int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n,
     if (batch == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 64) return lvae_potri_big_abi(Lc, Ainv, n, batch_stride, batch, st);
+    if (n <= 32 && batch >= 64) {
+        static bool attr = false;
+        const size_t smem = sizeof(double) * SMALL_WARPS * 2 * n * (n | 1);
+        if (!attr) {                                        // n = 32 needs 66 KB: above the 48 KB default
+            cudaError_t ea = cudaFuncSetAttribute(k_potri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)(sizeof(double) * SMALL_WARPS * 2 * 32 * 33));
+            if (ea != cudaSuccess) return lvae_cuda_rc(ea);
+            attr = true;
+        }
+        k_potri_warp<<<(batch + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, smem, st>>>(Lc, Ainv, n, batch_stride, batch);
+        LVAE_COUNT_LAUNCH();
+        return lvae_cuda_rc(cudaGetLastError());
+    }
     double* tmp = nullptr;
     cudaError_t e = lvae_scratch_alloc((void**)&tmp, sizeof(double) * (size_t)batch * n * n, st);
     if (e != cudaSuccess) return lvae_cuda_rc(e);

@@ -86,7 +86,9 @@ def test_blocks_api_matches_dense():
         assert rel(got, ref) < 1e-14
 
 
-@pytest.mark.parametrize("n,batch", [(5, 3), (20, 64), (60, 8), (72, 4), (256, 2)])
+# batch >= 64 with n <= 32 takes the warp-per-matrix kernels, the rest one CTA per matrix (n <= 64) or the blocked path
+@pytest.mark.parametrize("n,batch", [(5, 3), (20, 64), (60, 8), (72, 4), (256, 2), (1, 64), (8, 203), (31, 70), (32, 130),
+                                     (20, 5000)])
 def test_cholesky_and_inverse_vs_torch(n, batch):
     from lvae_b200 import ops
     g = torch.Generator().manual_seed(n)
