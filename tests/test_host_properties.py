@@ -1,0 +1,95 @@
+"""CPU: property tests (hypothesis) of the integer / index work on the path — bit-exact against the oracle's restatement of
+utils.py:40-113 and elbo_functions.py:264-267 on random shapes, not just the committed golden cases."""
+import numpy as np
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+from torch.utils.data.sampler import BatchSampler
+
+import lvae_oracle as orc
+from lvae_b200.utils import HensmanDataLoader, SubjectSampler, VaryingLengthBatchSampler, VaryingLengthSubjectSampler
+
+CFG = dict(max_examples=60, deadline=None)
+
+
+def _perm(seed, P):
+    np.random.seed(seed)
+    r = np.arange(P)
+    np.random.shuffle(r)
+    return r
+
+
+@settings(**CFG)
+@given(P=st.integers(1, 40), T=st.integers(1, 12), spb=st.integers(1, 45), seed=st.integers(0, 2**31 - 1))
+def test_fixed_T_sampler_and_batches(P, T, spb, seed):
+    perm = _perm(seed, P)
+    np.random.seed(seed)
+    rows = list(iter(SubjectSampler(list(range(P * T)), P, T)))
+    assert rows == orc.subject_sampler_rows(perm, T)
+    np.random.seed(seed)
+    batches = list(BatchSampler(SubjectSampler(list(range(P * T)), P, T), spb * T, drop_last=False))
+    assert batches == orc.fixed_T_batches(perm, T, spb)
+    # every batch holds whole subjects; only the last one may be short (training.py:114: P_in_current_batch = N_batch // T)
+    assert all(len(b) % T == 0 for b in batches) and all(len(b) == spb * T for b in batches[:-1])
+    assert sorted(r for b in batches for r in b) == list(range(P * T))
+
+
+@settings(**CFG)
+@given(lens=st.lists(st.integers(1, 9), min_size=1, max_size=25), spb=st.integers(1, 30), seed=st.integers(0, 2**31 - 1),
+       relabel=st.booleans())
+def test_varying_T_sampler_and_batches(lens, spb, seed, relabel):
+    P = len(lens)
+    labels = np.arange(P)
+    if relabel:                                   # ids need not be 0..P-1 nor sorted: subjects are numbered by first appearance
+        labels = np.random.default_rng(seed).permutation(P) * 3 + 5
+    ids = np.repeat(labels, lens)
+    data = [{'label': torch.tensor([0.0, float(i), 1.0])} for i in ids]
+    vs = VaryingLengthSubjectSampler(data, 1)
+    starts, ends = orc.varying_T_index(ids)
+    assert vs.start_indices == starts and vs.end_indices == ends and len(vs) == P
+    perm = _perm(seed, P)
+    np.random.seed(seed)
+    batches = list(iter(VaryingLengthBatchSampler(vs, spb)))
+    assert batches == orc.varying_T_batches(ids, perm, spb)
+    assert sorted(r for b in batches for r in b) == list(range(len(ids)))
+    subj_of_row = np.repeat(np.arange(P), lens)
+    assert all(len(set(subj_of_row[b].tolist())) == spb for b in batches[:-1])
+
+
+@settings(**CFG)
+@given(ids=st.lists(st.integers(0, 12), min_size=1, max_size=80))
+def test_group_by_subject_any_row_order(ids):
+    from lvae_b200.elbo_functions import group_by_subject
+    ids = np.asarray(ids, dtype=np.float64)
+    order, offsets, T_max, sum_T2 = group_by_subject(torch.from_numpy(ids))
+    uniq, rows = orc.group_rows_by_subject(ids)
+    lens = np.array([len(r) for r in rows])
+    want = np.concatenate(rows)
+    got = np.arange(len(ids)) if order is None else order.numpy()
+    assert np.array_equal(got, want)                      # subjects ascending, rows of a subject in their original order
+    assert np.array_equal(offsets.numpy(), np.concatenate([[0], np.cumsum(lens)]))
+    assert T_max == lens.max() and sum_T2 == int((lens * lens).sum())
+    assert np.array_equal(group_by_subject.last_counts, lens)
+
+
+def test_hensman_loader_repeats_epochs_without_restarting():
+    """utils.py:9-38: len = batches per epoch; one persistent iterator, so a new `for` continues with a new permutation."""
+    P, T, spb = 7, 3, 3
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return P * T
+
+        def __getitem__(self, i):
+            return {'idx': torch.tensor(i)}
+
+    np.random.seed(3)
+    dl = HensmanDataLoader(DS(), batch_sampler=BatchSampler(SubjectSampler(DS(), P, T), spb * T, drop_last=False),
+                           num_workers=0)
+    assert len(dl) == 3
+    epochs = [[b['idx'].tolist() for b in dl] for _ in range(3)]
+    np.random.seed(3)
+    for ep in epochs:
+        r = np.arange(P)
+        np.random.shuffle(r)
+        assert ep == orc.fixed_T_batches(r, T, spb)
