@@ -256,9 +256,46 @@ def _need_cuda(x):
         raise RuntimeError("lvae_b200: the GP-prior bounds need CUDA tensors (no CPU fallback)")
 
 
-def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps):
+def _stack_latents(modules0, modules1, likelihoods, device):
+    """(structure, lengthscale [n_ls,L], outputscale [n_comp,L], noise [L]) from L UN-batched kernel modules of identical
+    structure (the per-latent lists `covar_module0[i]`, `covar_module1[i]`, `likelihoods[i]` of the non-Hensman loops,
+    LVAE.py:244-270): latent l's hyper-parameters become column l of the tables, differentiably."""
+    from .spec import FlatComponent, _val
+    L = len(modules0)
+    if not (L == len(modules1) == len(likelihoods)) or L == 0:
+        raise RuntimeError("lvae_b200: need one (covar_module0, covar_module1, likelihood) triple per latent dimension")
+
+    def col(t):
+        t = _val(t).reshape(-1)
+        if t.numel() != 1:
+            raise RuntimeError("lvae_b200: the per-latent modules must be un-batched (one value per hyper-parameter)")
+        return t
+
+    def merge(per_latent):
+        out = []
+        for ci, first in enumerate(per_latent[0]):
+            shape = [(k, d) for k, d, _ in first.factors]
+            cs = [pl[ci] for pl in per_latent]
+            if any(len(pl) != len(per_latent[0]) for pl in per_latent) or \
+                    any([(k, d) for k, d, _ in c.factors] != shape or (c.outputscale is None) != (first.outputscale is None)
+                        for c in cs):
+                raise RuntimeError("lvae_b200: the per-latent kernel modules must share one structure")
+            os_ = None if first.outputscale is None else torch.cat([col(c.outputscale) for c in cs])
+            factors = [(k, d, None if ls is None else torch.cat([col(c.factors[fi][2]) for c in cs]))
+                       for fi, (k, d, ls) in enumerate(first.factors)]
+            out.append(FlatComponent(os_, factors))
+        return out
+
+    st, ls, os_ = build_structure(merge([flatten(m) for m in modules0]), merge([flatten(m) for m in modules1]), L,
+                                  device=device)
+    noise = torch.cat([_noise_of(lk, 1, torch.float64, device) for lk in likelihoods])
+    return st, ls, os_, noise
+
+
+def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps, hyper=None):
     """Shared pieces of elbo / deviance_upper_bound, per latent l (FP64, on x's device):
-    K0xz [L,N,M], iB [L*P,T,T], iB_K0xz [L,N,M], S = K0zx iB K0xz, iW = (Kzz + S)^-1, the summed log-dets, tr."""
+    K0xz [L,N,M], iB [L*P,T,T], iB_K0xz [L,N,M], S = K0zx iB K0xz, iW = (Kzz + S)^-1, the summed log-dets, tr.
+    hyper: precomputed (structure, lengthscale, outputscale, noise) instead of the three modules."""
     from . import diff_ops as D
     _need_cuda(x)
     f64 = torch.float64
@@ -270,8 +307,12 @@ def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps
     N, M = x.shape[0], z.shape[1]
     if N != P * T:
         raise RuntimeError(f"shape '[{P}, {T}, {x.shape[1]}]' is invalid for input of size {x.numel()}")
-    st, ls, os_ = _structure_of(covar_module0, covar_module1, L, x.device)
-    noise = _noise_of(likelihood, L, f64, x.device).contiguous()
+    if hyper is not None:
+        st, ls, os_, noise = hyper
+        noise = noise.contiguous()
+    else:
+        st, ls, os_ = _structure_of(covar_module0, covar_module1, L, x.device)
+        noise = _noise_of(likelihood, L, f64, x.device).contiguous()
     offsets = torch.arange(0, N + 1, T, dtype=torch.int32, device=x.device)
     eye = torch.eye(M, dtype=f64, device=x.device)
     K0xz = D.KernelDense.apply(st, "k0", x, z, ls, os_, None)
@@ -300,10 +341,10 @@ def _quad_form(t, y, L, P, T):
     return qF1 - qF2
 
 
-def _dubo_per_latent(L, covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, P, T, eps):
+def _dubo_per_latent(L, covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, P, T, eps, hyper=None):
     """elbo_functions.py:90-142 / validation.py:8-68 for all latents at once; m, log_v [N,L] (or [N] for L = 1)."""
     from . import diff_ops as D
-    t = _low_rank_terms(L, covar_module0, covar_module1, likelihood, train_xt, z, P, T, eps)
+    t = _low_rank_terms(L, covar_module0, covar_module1, likelihood, train_xt, z, P, T, eps, hyper)
     f64 = torch.float64
     mL = m.to(f64).reshape(t["N"], L).t().contiguous()
     lv = log_v.to(f64).reshape(t["N"], L).t().contiguous()
@@ -321,15 +362,42 @@ def deviance_upper_bound(covar_module0, covar_module1, likelihood, train_xt, m, 
     return _dubo_per_latent(1, covar_module0, covar_module1, likelihood, train_xt, m, log_v, z, P, T, eps).reshape(())
 
 
+def _elbo_per_latent(L, covar_module0, covar_module1, likelihood, train_xt, train_yt, z, P, T, eps, hyper=None):
+    import math
+    t = _low_rank_terms(L, covar_module0, covar_module1, likelihood, train_xt, z, P, T, eps, hyper)
+    y = train_yt.to(torch.float64).reshape(t["N"], L).t().contiguous()
+    qF = _quad_form(t, y, L, P, T)
+    logLike = -0.5 * T * P * math.log(2 * math.pi) - 0.5 * (t["logDet"] + qF)
+    return logLike - 0.5 * t["tr"]
+
+
 def elbo(covar_module0, covar_module1, likelihood, train_xt, train_yt, z, P, T, eps):
     """Low-rank evidence lower bound of one latent dimension given a latent sample (elbo_functions.py:36-88);
     differentiable w.r.t. the sample, the kernel hyper-parameters and the noise."""
-    import math
-    t = _low_rank_terms(1, covar_module0, covar_module1, likelihood, train_xt, z, P, T, eps)
-    y = train_yt.to(torch.float64).reshape(1, t["N"])
-    qF = _quad_form(t, y, 1, P, T)
-    logLike = -0.5 * T * P * math.log(2 * math.pi) - 0.5 * (t["logDet"] + qF)
-    return (logLike - 0.5 * t["tr"]).reshape(())
+    return _elbo_per_latent(1, covar_module0, covar_module1, likelihood, train_xt, train_yt, z, P, T, eps).reshape(())
+
+
+def _z_stack(zt_list):
+    return zt_list if torch.is_tensor(zt_list) else torch.stack([z for z in zt_list])
+
+
+def deviance_upper_bound_all(covar_modules0, covar_modules1, likelihoods, train_xt, m, log_v, zt_list, P, T, eps):
+    """The per-latent loop of training.py:334-343 / 537-546 / 654 / 730 as ONE batched evaluation (not in the reference):
+    `covar_modules0[i]`, `covar_modules1[i]`, `likelihoods[i]`, `zt_list[i]` are the un-batched per-latent objects of the
+    non-Hensman path, m / log_v are [N, L].  Returns the [L] vector whose entry i equals
+    deviance_upper_bound(covar_modules0[i], covar_modules1[i], likelihoods[i], train_xt, m[:, i], log_v[:, i], zt_list[i], ...);
+    `.sum()` is the reference's accumulated gp_loss.  Differentiable like the single-latent function."""
+    L = len(covar_modules0)
+    hyper = _stack_latents(covar_modules0, covar_modules1, likelihoods, train_xt.device)
+    return _dubo_per_latent(L, None, None, None, train_xt, m, log_v, _z_stack(zt_list), P, T, eps, hyper)
+
+
+def elbo_all(covar_modules0, covar_modules1, likelihoods, train_xt, Z, zt_list, P, T, eps):
+    """The per-latent loop of training.py:324-329 / 529-535 as one batched evaluation: entry i of the returned [L] vector is
+    elbo(covar_modules0[i], covar_modules1[i], likelihoods[i], train_xt, Z[:, i], zt_list[i], P, T, eps)."""
+    L = len(covar_modules0)
+    hyper = _stack_latents(covar_modules0, covar_modules1, likelihoods, train_xt.device)
+    return _elbo_per_latent(L, None, None, None, train_xt, Z, _z_stack(zt_list), P, T, eps, hyper)
 
 
 def KL_closed(covar_module, train_x, likelihoods, data, mu, log_var):

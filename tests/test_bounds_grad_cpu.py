@@ -5,7 +5,7 @@ which term).  The CUDA kernels under the same Functions are checked by tests/tes
 import pytest
 import torch
 
-from bounds_grad_check import CASES, check_case
+from bounds_grad_check import CASES, check_batched_over_latent_lists, check_case
 from ops_emulation import emulated_ops
 
 
@@ -13,6 +13,12 @@ from ops_emulation import emulated_ops
 def test_bounds_values_and_gradients_match_reference_golden(name):
     with emulated_ops():
         check_case(name, "cpu")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_batched_evaluation_of_per_latent_module_lists(name):
+    with emulated_ops():
+        check_batched_over_latent_lists(name, "cpu")
 
 
 def test_emulation_is_removed_afterwards_and_product_path_fails_loudly():

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from bounds_grad_check import CASES, check_case
+from bounds_grad_check import CASES, check_batched_over_latent_lists, check_case
 from conftest import load_golden
 from helpers import rel
 
@@ -15,6 +15,11 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_bounds_values_and_gradients_match_reference_golden(name):
     check_case(name, "cuda")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_batched_evaluation_of_per_latent_module_lists(name):
+    check_batched_over_latent_lists(name, "cuda")
 
 
 @pytest.mark.parametrize("which", ["k0", "k1", "all"])
