@@ -260,7 +260,7 @@ def _stack_latents(modules0, modules1, likelihoods, device):
     """(structure, lengthscale [n_ls,L], outputscale [n_comp,L], noise [L]) from L UN-batched kernel modules of identical
     structure (the per-latent lists `covar_module0[i]`, `covar_module1[i]`, `likelihoods[i]` of the non-Hensman loops,
     LVAE.py:244-270): latent l's hyper-parameters become column l of the tables, differentiably."""
-    from .spec import FlatComponent, _val
+    from .spec import FlatComponent, Raw, _val
     L = len(modules0)
     if not (L == len(modules1) == len(likelihoods)) or L == 0:
         raise RuntimeError("lvae_b200: need one (covar_module0, covar_module1, likelihood) triple per latent dimension")
@@ -271,6 +271,14 @@ def _stack_latents(modules0, modules1, likelihoods, device):
             raise RuntimeError("lvae_b200: the per-latent modules must be un-batched (one value per hyper-parameter)")
         return t
 
+    def stack(entries):
+        """One [L] entry from the L per-latent ones.  Lazy entries (raw parameter + constraint) stay lazy: their raw values
+        are concatenated and build_structure applies ONE transform to the whole table instead of one per module."""
+        if all(isinstance(e, Raw) and e.param.numel() == 1 for e in entries) and \
+                len({(e.kind, e.lower) for e in entries}) == 1:
+            return Raw(torch.cat([e.param.reshape(1) for e in entries]), entries[0].kind, entries[0].lower)
+        return torch.cat([col(e) for e in entries])
+
     def merge(per_latent):
         out = []
         for ci, first in enumerate(per_latent[0]):
@@ -280,16 +288,15 @@ def _stack_latents(modules0, modules1, likelihoods, device):
                     any([(k, d) for k, d, _ in c.factors] != shape or (c.outputscale is None) != (first.outputscale is None)
                         for c in cs):
                 raise RuntimeError("lvae_b200: the per-latent kernel modules must share one structure")
-            os_ = None if first.outputscale is None else torch.cat([col(c.outputscale) for c in cs])
-            factors = [(k, d, None if ls is None else torch.cat([col(c.factors[fi][2]) for c in cs]))
+            os_ = None if first.outputscale is None else stack([c.outputscale for c in cs])
+            factors = [(k, d, None if ls is None else stack([c.factors[fi][2] for c in cs]))
                        for fi, (k, d, ls) in enumerate(first.factors)]
             out.append(FlatComponent(os_, factors))
         return out
 
-    st, ls, os_ = build_structure(merge([flatten(m) for m in modules0]), merge([flatten(m) for m in modules1]), L,
-                                  device=device)
-    noise = torch.cat([_noise_of(lk, 1, torch.float64, device) for lk in likelihoods])
-    return st, ls, os_, noise
+    st, ls, os_, nz = build_structure(merge([flatten(m) for m in modules0]), merge([flatten(m) for m in modules1]), L,
+                                      device=device, extra=[stack([_noise_entry(lk) for lk in likelihoods])])
+    return st, ls, os_, nz.reshape(L).to(torch.float64)
 
 
 def _low_rank_terms(L, covar_module0, covar_module1, likelihood, x, z, P, T, eps, hyper=None):

@@ -81,6 +81,34 @@ def main():
     err = max(float((g - p.grad).abs().max() / p.grad.abs().max().clamp_min(1e-300)) for g, p in zip(g_own, params))
     out["max_rel_grad_diff_vs_stock_torch"] = err
     out["subjects_per_s_dubo_fwd_bwd"] = P / out["dubo_fwd_bwd_ms"] * 1e3
+    # the non-Hensman loops' pattern: per-latent un-batched module lists, one deviance_upper_bound call per latent
+    # (training.py:334-343) against ONE deviance_upper_bound_all call over the same lists
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200.kernel_gen import generate_kernel_approx
+    trip = []
+    for _ in range(L):
+        u0, u1 = generate_kernel_approx(**b.lists, id_covariate=2)
+        trip.append((u0.double().to(dev), u1.double().to(dev),
+                     GaussianLikelihood(noise_constraint=GreaterThan(1e-8)).double().to(dev)))
+    c0, c1, lk = [t[0] for t in trip], [t[1] for t in trip], [t[2] for t in trip]
+    zl = [z[i].contiguous() for i in range(L)]
+    lparams = [mu, lv] + [p for t in trip for mod in t for p in mod.parameters()]
+
+    def loop_step():
+        for p in lparams:
+            p.grad = None
+        tot = 0.0
+        for i in range(L):
+            tot = tot + EF.deviance_upper_bound(c0[i], c1[i], lk[i], x, mu[:, i], lv[:, i], zl[i], P, T, 1e-6)
+        tot.backward()
+
+    def all_step():
+        for p in lparams:
+            p.grad = None
+        EF.deviance_upper_bound_all(c0, c1, lk, x, mu, lv, zl, P, T, 1e-6).sum().backward()
+
+    out["per_latent_loop_dubo_fwd_bwd_ms"] = timed(loop_step, max(2, a.steps // 3), warmup=1)
+    out["dubo_all_fwd_bwd_ms"] = timed(all_step, a.steps)
     line = json.dumps(out)
     print(line)
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
