@@ -30,3 +30,53 @@ def test_emulation_is_removed_afterwards_and_product_path_fails_loudly():
     x = torch.zeros(4, 6, dtype=torch.float64)
     with pytest.raises(RuntimeError, match="CUDA"):
         EF.deviance_upper_bound(None, None, None, x, x[:, 0], x[:, 0], x[:2], 2, 2, 1e-6)
+
+
+def test_bounds_gradients_agree_with_central_differences():
+    """Independent of any golden file: d(sum DUBO)/d(theta) and d(sum ELBO)/d(theta) from the autograd Functions of diff_ops.py
+    against central differences, for every raw kernel / noise parameter and for entries of mu, log_v and the latent sample
+    (tiny well-conditioned problem, torch stand-ins for the C-ABI ops)."""
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200 import synth
+    from lvae_b200.constraints import GreaterThan
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200.likelihoods import GaussianLikelihood
+    L, P, T, M = 2, 3, 4, 5
+    b = synth.make_batch("cfg4", P=P, L=L, M=M, T=T)
+    z = b.z.clone()
+    z[:, :, 0] += 0.37 * torch.arange(M, dtype=torch.float64)          # distinct inducing inputs: well-conditioned Kzz
+    torch.manual_seed(0)
+    cm0, cm1 = generate_kernel_batched(L, **b.lists, id_covariate=2)
+    cm0, cm1 = cm0.double(), cm1.double()
+    lik = GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=GreaterThan(1e-8)).double()
+    params = [p for m in (cm0, cm1, lik) for p in m.parameters()]
+    with torch.no_grad():
+        for p in params:
+            p.add_(0.3 * torch.randn_like(p))
+    mu, lv = b.mu.clone().requires_grad_(True), b.log_v.clone().requires_grad_(True)
+
+    def dubo():
+        return EF._dubo_per_latent(L, cm0, cm1, lik, b.x, mu, lv, z, P, T, 1e-3).sum()
+
+    def elbo():
+        return EF._elbo_per_latent(L, cm0, cm1, lik, b.x, mu, z, P, T, 1e-3).sum()
+
+    with emulated_ops():
+        for f, leaves in ((dubo, [mu, lv]), (elbo, [mu])):
+            for t in params + leaves:
+                t.grad = None
+            f().backward()
+            for t in params + leaves:
+                g = t.grad.reshape(-1)
+                flat = t.data.reshape(-1)
+                for idx in sorted({0, flat.numel() // 2, flat.numel() - 1}):
+                    h = 1e-5
+                    old = float(flat[idx])
+                    with torch.no_grad():
+                        flat[idx] = old + h
+                        fp = float(f())
+                        flat[idx] = old - h
+                        fm = float(f())
+                        flat[idx] = old
+                    fd = (fp - fm) / (2 * h)
+                    assert abs(fd - float(g[idx])) <= 1e-6 * max(1.0, abs(fd)), (f.__name__, tuple(t.shape), idx, fd, float(g[idx]))
