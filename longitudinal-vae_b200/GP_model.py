@@ -29,23 +29,36 @@ def _bounded(raw, min_log):
     return torch.exp(min_log + F.softplus(raw - min_log))
 
 
+_FLOOR = -16.0
+
+
+def _add_bounded(module, raw_name, floor_name, value, latent_dim, trainable=True):
+    """Registers `raw_name` ([latent_dim] parameter, float32 like the reference's) and the `floor_name` buffer so that
+    exp(floor + softplus(raw - floor)) starts at `value`."""
+    floor = torch.full((1,), _FLOOR)
+    start = torch.log(torch.as_tensor(value, dtype=torch.float32) - torch.exp(floor)).reshape(())
+    setattr(module, raw_name, nn.Parameter(start.repeat(latent_dim), requires_grad=trainable))
+    module.register_buffer(floor_name, floor)
+
+
+def _bounded_property(raw_name, floor_name):
+    """value = exp(floor + softplus(raw - floor)); assigning a value re-initialises the raw parameter."""
+    def read(self):
+        return _bounded(getattr(self, raw_name), getattr(self, floor_name))
+
+    def write(self, value):
+        with torch.no_grad():
+            getattr(self, raw_name).copy_(torch.log(torch.as_tensor(value) - torch.exp(getattr(self, floor_name))))
+    return property(read, write)
+
+
 class Likelihoods(nn.Module):
     def __init__(self, latent_dim, noise, constrain=True):
         super().__init__()
         self.latent_dim = latent_dim
-        min_log_noise = torch.Tensor([-16.0])
-        init = torch.log(torch.as_tensor(noise, dtype=torch.float32) - torch.exp(min_log_noise))
-        self._log_noise = nn.Parameter(torch.Tensor([init] * latent_dim), requires_grad=constrain)
-        self.register_buffer('min_log_noise', min_log_noise * torch.ones(1))
+        _add_bounded(self, '_log_noise', 'min_log_noise', noise, latent_dim, trainable=constrain)
 
-    @property
-    def noise(self):
-        return _bounded(self._log_noise, self.min_log_noise)
-
-    @noise.setter
-    def noise(self, noise):
-        with torch.no_grad():
-            self._log_noise.copy_(torch.log(torch.as_tensor(noise) - torch.exp(self.min_log_noise)))
+    noise = _bounded_property('_log_noise', 'min_log_noise')
 
 
 class _DenseModule(nn.Module):
@@ -82,19 +95,9 @@ class RbfKernel(_DenseModule):
         super().__init__()
         self.dim = dim
         self.latent_dim = latent_dim
-        min_log = torch.Tensor([-16.0])
-        init = torch.log(torch.as_tensor(lengthscale, dtype=torch.float32) - torch.exp(min_log))
-        self._log_lengthscale = nn.Parameter(torch.Tensor([init] * latent_dim), requires_grad=True)
-        self.register_buffer('min_log_lengthscale', min_log * torch.ones(1))
+        _add_bounded(self, '_log_lengthscale', 'min_log_lengthscale', lengthscale, latent_dim)
 
-    @property
-    def lengthscale(self):
-        return _bounded(self._log_lengthscale, self.min_log_lengthscale)
-
-    @lengthscale.setter
-    def lengthscale(self, lengthscale):
-        with torch.no_grad():
-            self._log_lengthscale.copy_(torch.log(torch.as_tensor(lengthscale) - torch.exp(self.min_log_lengthscale)))
+    lengthscale = _bounded_property('_log_lengthscale', 'min_log_lengthscale')
 
     def _flat_components(self):
         return [FlatComponent(None, [('rbf', self.dim, Raw(self._log_lengthscale, 'bounded', _min_float(self, 'min_log_lengthscale')))])]
@@ -105,19 +108,9 @@ class ScaleKernel(_DenseModule):
         super().__init__()
         self.latent_dim = latent_dim
         self.kernel = kernel
-        min_log = torch.Tensor([-16.0])
-        init = torch.log(torch.as_tensor(scale, dtype=torch.float32) - torch.exp(min_log))
-        self._log_scale = nn.Parameter(torch.Tensor([init] * latent_dim), requires_grad=True)
-        self.register_buffer('min_log_scale', min_log * torch.ones(1))
+        _add_bounded(self, '_log_scale', 'min_log_scale', scale, latent_dim)
 
-    @property
-    def scale(self):
-        return _bounded(self._log_scale, self.min_log_scale)
-
-    @scale.setter
-    def scale(self, scale):
-        with torch.no_grad():
-            self._log_scale.copy_(torch.log(torch.as_tensor(scale) - torch.exp(self.min_log_scale)))
+    scale = _bounded_property('_log_scale', 'min_log_scale')
 
     def _flat_components(self):
         s = FlatComponent(Raw(self._log_scale, 'bounded', _min_float(self, 'min_log_scale')), [])

@@ -52,10 +52,6 @@ class CatKernelMod(Kernel):
 
 
 def RbfKernel(active_dims, batch_shape=None):
-    """RBF kernel on one covariate column with lengthscale initialised to 2.5 (kernel_spec.py:58-69)."""
-    if batch_shape is None:
-        k = RBFKernel(active_dims=active_dims)
-    else:
-        k = RBFKernel(active_dims=active_dims, batch_shape=batch_shape)
-    k.initialize(lengthscale=2.5)
-    return k
+    """Squared-exponential kernel on one covariate column, lengthscale 2.5 per latent to start with (kernel_spec.py:58-69)."""
+    shape = {} if batch_shape is None else {"batch_shape": batch_shape}
+    return RBFKernel(active_dims=active_dims, **shape).initialize(lengthscale=2.5)
