@@ -8,9 +8,11 @@ sharded across GPUs, and one tail kernel.  `kld_total` is an autograd node w.r.t
 hyper-parameter, the likelihood noise and (natural_gradient=False) m and H; its gradients are produced by the same
 launches (closed-form adjoints) and scaled by the incoming gradient in backward.
 """
+import numpy as np
 import torch
 
 from . import ops
+from ._lib import MAX_M, MAX_T
 from .spec import build_structure, flatten
 
 _GROUP = None        # torch.distributed process group over which the minibatch subjects are sharded (None = 1 GPU)
@@ -138,8 +140,7 @@ def _structure_of(covar_module0, covar_module1, L, device):
 
 def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets, T_max, sum_T2, mu, log_v, z, scale,
          const_term, natural_gradient, eps, counts=None):
-    if not x.is_cuda:
-        raise RuntimeError("lvae_b200: the GP-prior ELBO op needs CUDA tensors (no CPU fallback)")
+    _need_cuda(x)
     L = latent_dim
     f64 = torch.float64
     st, ls, os_, nz = build_structure(flatten(covar_module0), flatten(covar_module1), L, device=x.device,
@@ -149,6 +150,13 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
     hyper = ls._base if same else torch.cat([ls, os_, nz.reshape(1, L).to(f64)])
     if z.dim() == 2:
         z = z.unsqueeze(0).expand(L, -1, -1)
+    if int(T_max) > MAX_T:                                   # longer subjects than the fused kernels cover
+        if _GROUP is not None:
+            raise RuntimeError(f"lvae_b200: subjects with more than {MAX_T} rows are not supported in the sharded modes")
+        if counts is None:
+            counts = np.full(offsets.numel() - 1, int(T_max), dtype=np.int64)
+        return _composed_bound(st, ls, os_, nz.reshape(L), L, m, H, x, offsets, counts, mu, log_v, z, scale, const_term,
+                               natural_gradient, eps)
     meta = dict(structure=st, x=x.to(f64), z=z.to(f64), offsets=offsets, L=L, T_max=int(T_max), sum_T2=int(sum_T2),
                 scale=scale, const_term=const_term, eps=eps, natural_gradient=bool(natural_gradient), counts=counts)
     if _GROUP is not None and _SHARD == "latents":
@@ -159,6 +167,68 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
         gH._lvae_hinv = meta.get("Hinv")
         return kld, gm, gH
     return kld, None, None
+
+
+def _composed_bound(st, ls, os_, noise, L, m, H, x, offsets, counts, mu, log_v, z, scale, const_term, natural_gradient, eps):
+    """The same bound for subjects with MORE than 40 rows (up to 256), which the fused kernels do not cover: composed from the
+    differentiable CUDA ops of diff_ops.py (kernel matrices, batched SPD inverse / log-det, DMMA GEMM), autograd instead of
+    the closed-form adjoints.  Formulas: SURVEY 8(a) / elbo_functions.py:171-214, 264-305; subjects are processed in groups of
+    equal length (one batched factorisation per distinct T).  An order of magnitude slower per row than the fused path —
+    a correctness fallback, not a throughput path."""
+    from . import diff_ops as D
+    f64 = torch.float64
+    dev = x.device
+    x = x.detach().to(f64).contiguous()
+    z = z.detach().to(f64).contiguous()
+    N, M = x.shape[0], z.shape[1]
+    counts = np.asarray(counts, dtype=np.int64)
+    if int(counts.max()) > MAX_M:
+        raise RuntimeError(f"lvae_b200: a subject has {int(counts.max())} rows; the batched Cholesky covers up to {MAX_M}")
+    row0 = np.concatenate([[0], np.cumsum(counts)])
+    blk0 = np.concatenate([[0], np.cumsum(counts * counts)])
+    sum_T2 = int(blk0[-1])
+    muT, lvT = mu.to(f64).t().contiguous(), log_v.to(f64).t().contiguous()               # [L, N]
+    m3, H = m.to(f64).reshape(L, M, 1), H.to(f64)
+    noise = noise.to(f64).contiguous()
+    Kxz = D.KernelDense.apply(st, "k0", x, z, ls, os_, None)                              # [L, N, M]      (171)
+    Kzz = D.KernelDense.apply(st, "k0", z, z, ls, os_, None) + eps * torch.eye(M, dtype=f64, device=dev)   # (172, 176)
+    K0b = D.KernelBlocks.apply(st, "k0", x, offsets, sum_T2, ls, os_, None)               # flat [L, sum T^2]  (173)
+    Bb = D.KernelBlocks.apply(st, "k1", x, offsets, sum_T2, ls, os_, noise)               # K1 + noise I       (174)
+    Ki, ldK = D.spd_inverse(Kzz)                                                          # (177-178)
+    Hi, ldH = D.spd_inverse(H)                                                            # (185-186)
+    a = D.gemm(Ki, m3)
+    r = D.gemm(Kxz, a).reshape(L, N) - muT                                                # (189)
+    zero = torch.zeros(L, dtype=f64, device=dev)
+    S, ng1 = torch.zeros(L, M, M, dtype=f64, device=dev), torch.zeros(L, M, 1, dtype=f64, device=dev)
+    A, Bt, C, D1 = zero, zero, zero, zero
+    for T in np.unique(counts).tolist():
+        sel = np.nonzero(counts == T)[0]
+        PT = len(sel)
+        rows = torch.from_numpy((row0[sel][:, None] + np.arange(T)[None, :]).reshape(-1)).to(dev)
+        ent = torch.from_numpy((blk0[sel][:, None] + np.arange(T * T)[None, :]).reshape(-1)).to(dev)
+        iB, ldB = D.spd_inverse(Bb[:, ent].reshape(L * PT, T, T))                         # (179-180)
+        Kx = Kxz[:, rows].reshape(L * PT, T, M)
+        V = D.gemm(iB, Kx)                                                                # B^-1 Kxz
+        S = S + D.gemm(Kx.reshape(L, PT * T, M), V.reshape(L, PT * T, M), ta=True)        # (183-184)
+        rt = r[:, rows].reshape(L * PT, T, 1)
+        A = A + (rt * D.gemm(iB, rt)).reshape(L, -1).sum(1)                               # (190)
+        Bt = Bt + (torch.diagonal(iB, dim1=-2, dim2=-1).reshape(L, -1) * torch.exp(lvT[:, rows])).sum(1)       # (191)
+        C = C + ldB.reshape(L, PT).sum(1)                                                 # (192)
+        D1 = D1 + (iB * K0b[:, ent].reshape(L * PT, T, T)).reshape(L, -1).sum(1)          # (193), first term
+        ng1 = ng1 + D.gemm(V.reshape(L, PT * T, M), muT[:, rows].reshape(L, PT * T, 1), ta=True)               # (208)
+    Dt = D1 - (S * Ki).reshape(L, -1).sum(1)                                              # (193)
+    G = D.gemm(D.gemm(Ki, H), Ki)                                                         # (194)
+    E = (G * S).reshape(L, -1).sum(1)                                                     # (195 / 282)
+    F_ = lvT.sum(1)                                                                       # (196)
+    kl_u = 0.5 * ((Ki * H.transpose(1, 2)).reshape(L, -1).sum(1) + (m3 * a).reshape(L, -1).sum(1) - M + ldK - ldH)   # (199-203)
+    kld = (scale * 0.5 * (A + Bt + C + Dt + E - F_) + kl_u).sum() - const_term            # (204 / 299)
+    if not natural_gradient:
+        return kld, None, None
+    with torch.no_grad():                                                                 # (208-214 / 301-305)
+        Bm = D.gemm(D.gemm(Ki, S), Ki) + Ki
+        grad_m = D.gemm(Bm, m3) - D.gemm(Ki, ng1)
+        grad_H = 0.5 * (Bm - Hi)
+    return kld, grad_m, grad_H
 
 
 def latent_slice(L, rank, world):

@@ -80,3 +80,14 @@ def test_bounds_gradients_agree_with_central_differences():
                         flat[idx] = old
                     fd = (fp - fm) / (2 * h)
                     assert abs(fd - float(g[idx])) <= 1e-6 * max(1.0, abs(fd)), (f.__name__, tuple(t.shape), idx, fd, float(g[idx]))
+
+
+@pytest.mark.parametrize("ng", [True, False])
+def test_long_subjects_take_the_composed_path_and_match_the_oracle(ng):
+    """Subjects with more than 40 rows (the fused kernels' limit) go through elbo_functions._composed_bound, built from the
+    differentiable ops; with the ops swapped for torch stand-ins its formulas are checked here against the oracle's restatement
+    of minibatch_KLD_upper_bound_iter (elbo_functions.py:219-307): bound, natural gradients / d m, d H, d mu, d log_v and
+    the hyper-parameter gradients.  The same call on the CUDA ops: tests/test_gpu_bounds_grad.py."""
+    from long_subjects_check import check_long_subjects
+    with emulated_ops():
+        check_long_subjects("cpu", ng)

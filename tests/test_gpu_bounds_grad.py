@@ -122,3 +122,10 @@ def test_adam_on_dubo_follows_the_cpu_trajectory():
     assert got[0][-1] < got[0][0]                                   # it descends
     assert rel(np.asarray(got[0]), np.asarray(want[0])) < 1e-6
     assert rel(got[1], want[1]) < 1e-6 and rel(got[2], want[2]) < 1e-6
+
+
+@pytest.mark.parametrize("ng", [True, False])
+def test_long_subjects_take_the_composed_path_and_match_the_oracle(ng):
+    """More than 40 rows per subject (41..55 here): elbo_functions._composed_bound on the CUDA ops against the oracle."""
+    from long_subjects_check import check_long_subjects
+    check_long_subjects("cuda", ng)
