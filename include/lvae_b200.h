@@ -25,7 +25,7 @@ extern "C" {
 #define LVAE_MAX_COMPONENTS 16
 #define LVAE_MAX_MASKS 3
 #define LVAE_MAX_M 256
-#define LVAE_MAX_T 40
+#define LVAE_MAX_T 40 /* rows per subject in lvae_kld_*; the Python mirror composes longer subjects from the ops below */
 #define LVAE_SPEC_STRIDE 10
 
 /* factor types inside a component */
