@@ -99,7 +99,7 @@ int lvae_gemm_batched_f64(int32_t trans_a, int32_t trans_b, int32_t m, int32_t n
                           double* C, int32_t ldc, int64_t stride_c, int32_t batch, int32_t flags, void* stream);
 
 /* Batched Cholesky, in place, lower, n <= 256: replaces torch.cholesky (elbo_functions.py:177,179,185).
- * n <= 64: one CTA per matrix; n > 64: blocked by 64 (diagonal blocks in shared memory, panels and trailing updates as
+ * n <= 32 and at least 64 matrices: one warp per matrix in shared memory; n <= 64: one CTA per matrix; n > 64: blocked by 64 (diagonal blocks in shared memory, panels and trailing updates as
  * batched DMMA GEMMs; scratch from the stream-ordered allocator).
  * info: device int32[1], set to 1 + index of the first non-PD matrix (never cleared). */
 int lvae_potrf_batched_f64(double* A, int32_t n, int64_t batch_stride, int32_t batch, int32_t* info, void* stream);
