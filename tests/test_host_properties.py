@@ -93,3 +93,44 @@ def test_hensman_loader_repeats_epochs_without_restarting():
         r = np.arange(P)
         np.random.shuffle(r)
         assert ep == orc.fixed_T_batches(r, T, spb)
+
+
+_COV = st.integers(0, 5)
+
+
+@settings(max_examples=40, deadline=None)
+@given(cat=st.lists(_COV, max_size=3, unique=True), bin_=st.lists(_COV, max_size=2, unique=True),
+       sq=st.lists(_COV, max_size=3, unique=True),
+       cat_int=st.lists(st.tuples(_COV, _COV), max_size=3), bin_int=st.lists(st.tuples(_COV, _COV), max_size=2),
+       missing=st.lists(st.tuples(_COV, _COV), max_size=2, unique_by=lambda t: t[0]), id_cov=_COV)
+def test_block_indexing_rule_on_random_kernel_lists(cat, bin_, sq, cat_int, bin_int, missing, id_cov):
+    """kernel_gen.py:225-308 / GP_model.py:146-236 on random structure lists: K0/K1 assignment, component order, factor order
+    and missing-value masks of both generators equal the oracle's restatement, bit for bit."""
+    from lvae_b200 import GP_model
+    from lvae_b200.kernel_gen import generate_kernel_batched
+    from lvae_b200.spec import build_structure, flatten
+    lists = dict(cat_kernel=cat, bin_kernel=bin_, sqexp_kernel=sq,
+                 cat_int_kernel=[{'cont_covariate': c, 'cat_covariate': k} for c, k in cat_int],
+                 bin_int_kernel=[{'cont_covariate': c, 'bin_covariate': k} for c, k in bin_int],
+                 covariate_missing_val=[{'covariate': c, 'mask': m} for c, m in missing])
+    if id_cov not in cat and not any(k == id_cov for _, k in cat_int):
+        lists['cat_kernel'] = cat + [id_cov]     # the reference needs at least one component on either side
+    if not (lists['sqexp_kernel'] or bin_ or bin_int or any(d != id_cov for d in lists['cat_kernel'])
+            or any(k != id_cov for _, k in cat_int)):
+        lists['sqexp_kernel'] = [0]
+    k0, k1 = orc.parse_kernel_lists(2, **lists, id_covariate=id_cov)
+    assert k0 and k1
+    for gen in (generate_kernel_batched, GP_model.generate_kernel_batched):
+        cm0, cm1 = gen(2, **lists, id_covariate=id_cov)
+        stc, ls, os_ = build_structure(flatten(cm0), flatten(cm1), 2)
+        assert (stc.n_comp0, stc.n_comp1) == (len(k0), len(k1))
+        assert stc.n_ls == sum(len(c.lengthscales) for c in k0 + k1)
+        i_ls = 0
+        for row, comp in zip(stc.table, k0 + k1):
+            rbf = [d for kind, d in comp.factors if kind == 'rbf']
+            masks = [(0 if kind == 'cat' else 1, d) for kind, d in comp.factors if kind != 'rbf']
+            assert row[0] == (rbf[0] if rbf else -1) and row[2] == len(masks)
+            assert [(row[3 + 2 * i], row[4 + 2 * i]) for i in range(len(masks))] == masks
+            if rbf:
+                assert row[1] == i_ls
+                i_ls += 1
