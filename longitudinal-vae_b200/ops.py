@@ -330,8 +330,9 @@ def gemm_batched(A, B, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, C=None
     batch = A.shape[0]
     m, k = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
     n = B.shape[1] if trans_b else B.shape[2]
-    if C is None:
-        C = torch.zeros(batch, m, n, dtype=F64, device=A.device)
+    if C is None:               # every entry is written unless only the lower triangle is asked for (no memset of 300 MB outputs)
+        full = beta == 0.0 and (int(flags) & 3) != 1 and min(m, n) > 0
+        C = (torch.empty if full else torch.zeros)(batch, m, n, dtype=F64, device=A.device)
     with torch.cuda.device(A.device):
         rc = lib.lvae_gemm_batched_f64(int(trans_a), int(trans_b), m, n, k, float(alpha), ptr(A), A.shape[2],
                                        A.shape[1] * A.shape[2], ptr(B), B.shape[2], B.shape[1] * B.shape[2], float(beta),
