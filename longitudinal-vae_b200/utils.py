@@ -103,9 +103,9 @@ def _spd_inverse(A):
 def _predict_one(L, covar_module0, covar_module1, likelihoods, x, test_x, mu, z, id_covariate, eps):
     """x [N,Q] prediction (training) rows, mu [N,L], z [L,M,Q] | [M,Q]; returns Z_pred [N*, L]."""
     from . import ops
+    from . import elbo_functions as EF
     from .elbo_functions import _noise_of, _structure_of, group_by_subject
-    if not x.is_cuda:
-        raise RuntimeError("lvae_b200: prediction needs CUDA tensors (no CPU fallback)")
+    EF._need_cuda(x)                                                              # no CPU fallback
     f64 = torch.float64
     x, test_x, mu = x.to(f64), test_x.to(f64), mu.to(f64).reshape(x.shape[0], L)
     z = z.to(f64)

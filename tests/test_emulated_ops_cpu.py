@@ -91,3 +91,26 @@ def test_long_subjects_take_the_composed_path_and_match_the_oracle(ng):
     from long_subjects_check import check_long_subjects
     with emulated_ops():
         check_long_subjects("cpu", ng)
+
+
+@pytest.mark.parametrize("name", ["predict_fixed", "predict_ragged", "predict_m72"])
+def test_prediction_host_logic_matches_reference_golden(name):
+    """utils.batch_predict / batch_predict_varying_T above the ops (grouping by rows per subject, scatter back, the seen /
+    unseen-subject split of the K1 term) against the reference's Z_pred, with torch stand-ins for the C-ABI ops."""
+    from conftest import load_golden
+    from helpers import build_modules, rel
+    from lvae_b200 import utils as U
+    g = load_golden(name)
+    L = g["mu"].shape[1]
+    with emulated_ops():
+        cm0, cm1, lik = build_modules(g["lists"], L, g["lengthscale"], g["outputscale"], g["noise"], "cpu")
+        t = lambda k: torch.from_numpy(g[k].copy())
+        Zv = U.batch_predict_varying_T(L, cm0, cm1, lik, t("x"), t("test_x"), t("mu"), t("z"), 2, float(g["eps"]))
+        assert Zv.shape == g["Z_pred"].shape and rel(Zv, g["Z_pred"]) < 1e-6
+        if not bool(g["ragged"]):
+            P = len(g["offsets"]) - 1
+            Z = U.batch_predict(L, cm0, cm1, lik, t("x"), t("test_x"), t("mu"), t("z"), P, int(g["T"]), 2, float(g["eps"]))
+            assert rel(Z, g["Z_pred"]) < 1e-6
+        perm = torch.randperm(g["x"].shape[0], generator=torch.Generator().manual_seed(1))
+        Zp = U.batch_predict_varying_T(L, cm0, cm1, lik, t("x")[perm], t("test_x"), t("mu")[perm], t("z"), 2, float(g["eps"]))
+        assert rel(Zp, g["Z_pred"]) < 1e-6
