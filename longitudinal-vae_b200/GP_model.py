@@ -11,7 +11,6 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from . import ops
 from .spec import FlatComponent, Raw, build_structure, flatten, latent_count
 
 

@@ -10,7 +10,6 @@ no dense torch arithmetic — `.evaluate()` flattens the tree (spec.py) and runs
 import torch
 from torch.nn import ModuleList
 
-from . import ops
 from .constraints import Positive
 from .constraints import GreaterThan
 from .spec import FlatComponent, Raw, build_structure, flatten, latent_count

@@ -1,6 +1,4 @@
 """Drop-in for the reference's kernel_spec.py: leaf kernels of the additive GP prior."""
-import torch
-
 from .gp_kernels import Kernel, RBFKernel
 from .spec import FlatComponent
 

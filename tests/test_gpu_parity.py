@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_golden, oracle_components
+from conftest import GOLDEN_CASES, load_golden
 from helpers import build_modules, golden_hyper_vector, rel, run_cuda_case
 
 pytestmark = pytest.mark.gpu

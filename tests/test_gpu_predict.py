@@ -1,6 +1,5 @@
 """GPU parity of the prediction path against golden vectors produced by the reference's own
 utils.batch_predict / batch_predict_varying_T (oracle/make_golden_predict.py).  Tolerance 1e-6 relative (FP64)."""
-import numpy as np
 import pytest
 import torch
 

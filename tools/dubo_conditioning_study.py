@@ -2,7 +2,7 @@
 equivalent FP64 inverse algorithms (cholesky_inverse | linalg.inv | cholesky_solve(I)) drift apart at cfg2 scale, where
 Kzz = K0(Z,Z) + 1e-6 I has duplicated rows (cond ~ 1e8).  Result (P=300, L=4, M=60): value 3e-11, d mu / d log v 2e-9, K1 and noise
 gradients <= 1e-6, K0 outputscale / lengthscale gradients 1e-5 .. 2e-4 — the floor any FP64 implementation of this bound has."""
-import sys, torch, numpy as np
+import sys, torch
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import ops_emulation as emu
 from lvae_b200 import synth
