@@ -7,14 +7,17 @@
 A "step" is one Hensman minibatch of the path: kernel construction from covariates, batched Cholesky/inverse of the
 per-subject blocks and of K_mm/H, the minibatch KL upper bound, ALL its gradients (mu, log_v, kernel hyper-parameters,
 noise) and the natural-gradient update of (m, H)  (elbo_functions.py:144-216 + backward + training.py:129-135).
-Workload at N=1 = BASELINE.json configs[1]: Health-MNIST-shaped synthetic data, 1000 subjects x 20 time points, L=32,
-M=60, full additive kernel (cat(id) + SE(age) + id x age + gender x age + disease x disease_time), all 1000 subjects in
-one minibatch per step.  N>1: weak scaling — every rank holds its own 1000 subjects of a N*1000-subject minibatch and
-the SVGP sufficient statistics are all-reduced over NCCL between the subject pass and the tail.
+Headline workload = BASELINE.json configs[1] (cfg2): Health-MNIST-shaped synthetic data, 1000 subjects x 20 time points
+per GPU, L=32, M=60, full additive kernel (cat(id) + SE(age) + id x age + gender x age + disease x disease_time), all
+subjects of a rank in one minibatch per step.  N>1: weak scaling — every rank holds its own 1000 subjects of a N*1000
+-subject minibatch and the SVGP sufficient statistics are summed over ranks between the subject pass and the tail.
 
 `value` is device-resident throughput (inputs in HBM, CUDA events, max over ranks); `e2e` is the same step through the
 public Python API (lvae_b200.elbo_functions.minibatch_KLD_upper_bound + backward + natural_gradient_step) with pinned
-HOST inputs copied in and the loss and encoder gradients copied out inside the timed region.
+HOST inputs copied in and the loss and encoder gradients copied out inside the timed region.  `parity` compares the
+outputs of the CUDA path ON THE TIMED PROBLEM with the oracle port of the reference run with stock torch ops on the same
+GPU (and, for N > 1, the sharded result with a one-GPU evaluation of the gathered minibatch); a failed check exits 1.
+`other_configs` carries the same measurements for BASELINE configs[2..4] (cfg3, cfg4, cfg5) and a strong-scaling point.
 """
 import argparse
 import json
@@ -32,6 +35,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gp_prior_elbo_step_subjects_per_sec"
 UNIT = "subjects/s"
+LR = 1e-3
+EPS = 1e-6
+# Parity tolerances, max-norm relative per output tensor (north_star: 1e-6 FP64).  The K0 hyper-parameter gradients are
+# differences of terms ~1/eps larger than the result when cond(Kzz + eps I) ~ 1e8: the hyper-
+# gradient VECTOR is compared per latent-stacked vector at 1e-6 of its max-norm like the other tensors, and its
+# worst single entry is reported next to it (not gated).
+TOL = 1e-6
 
 
 def parse():
@@ -41,16 +51,24 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", default="cfg2")
-    ap.add_argument("--spb", type=int, default=1000, help="subjects per minibatch per GPU")
+    ap.add_argument("--spb", type=int, default=None, help="subjects per minibatch per GPU (default: per config)")
     ap.add_argument("--L", type=int, default=None)
     ap.add_argument("--M", type=int, default=None)
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic kernels, 2 fused DMMA kernel")
-    ap.add_argument("--cpu-subjects", type=int, default=100, help="subjects in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-subjects", type=int, default=None,
+                    help="subjects in the CPU arm's per-step sample (default: the whole minibatch of one rank for fixed T "
+                         "and M <= 64, else 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
                     help="N > 1: statistics exchange by NCCL all-reduce or by the peer-memory kernel (symmetric memory)")
     ap.add_argument("--no-latency-point", action="store_true", help="skip the spb=20 point (the reference's default batch)")
+    ap.add_argument("--no-others", action="store_true", help="skip cfg3 / cfg4 / cfg5 and the strong-scaling point")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--others-steps", type=int, default=5)
     return ap.parse_args()
+
+
+DEFAULT_SPB = {"cfg1": 100, "cfg2": 1000, "cfg3": 1000, "cfg4": 2500, "cfg5": 2000}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -63,6 +81,31 @@ def make_problem(cfg, spb, rank, world, L=None, M=None):
         b0 = synth.make_batch(cfg, P=spb, L=L, M=M, seed=1234 + int(cfg[-1]))
         b.z, b.m, b.H = b0.z, b0.m, b0.H
     return b
+
+
+def n_components(lists):
+    return (len(lists["cat_kernel"]) + len(lists["sqexp_kernel"]) + len(lists["bin_kernel"]) + len(lists["cat_int_kernel"]) +
+            len(lists["bin_int_kernel"]))
+
+
+def workload_config(cfg, spb, world, b, strong=False):
+    """The `config` object — identical in both arms (ours and --impl reference) for the same flags."""
+    Tdesc = f"T={b.T}" if not isinstance(b.T, tuple) else f"T in {b.T[0]}..{b.T[1]} (ragged)"
+    glob = spb if strong else spb * world
+    return {"workload": f"{cfg}: Health-MNIST-shaped synthetic, {Tdesc}, L={b.L}, M={b.M}, additive kernel with "
+                        f"{n_components(b.lists)} components, one minibatch of {glob} subjects per step over {world} GPU(s) "
+                        f"(bound + all gradients + natural-gradient update), perturbed hyper-parameters",
+            "global_batch_subjects": glob, "L": b.L, "M": b.M, "n_gpus": world}
+
+
+def hyper_values(b):
+    """Perturbed hyper-parameters of SURVEY 8(d) (so that latents differ): (lengthscale [n_ls,L], outputscale [n_comp,L],
+    noise [L]) in K0-then-K1 component order."""
+    from lvae_b200 import synth
+    lists = b.lists
+    id_cov = 2
+    n_ls = len(lists["sqexp_kernel"]) + len(lists["cat_int_kernel"]) + len(lists["bin_int_kernel"])
+    return synth.perturbed_hypers(n_ls, n_components(lists), b.L, seed=1234, noise_trainable=True) + (id_cov,)
 
 
 def algorithmic_flops(T, L, M, C0, C1, P_b):
@@ -136,52 +179,163 @@ def dgemm_peak_tflops(device):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference, all host threads
+# The oracle port of the reference (oracle/lvae_oracle.py): the CHECKER of `parity`, the "existing GPU path" when run with
+# stock torch CUDA ops, and the CPU arm's fallback when baseline/_ref is absent.
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(b, n_subjects, device="cpu"):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+def _oracle():
+    p = os.path.join(ROOT, "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
     import lvae_oracle as orc
-    L, M = b.L, b.M
+    return orc
+
+
+def oracle_components(b, device, requires_grad=True):
+    """Oracle kernel components with this problem's hyper-parameters on `device`; returns (k0, k1, noise, params) with
+    params ordered [lengthscale rows | outputscale rows | noise] like the library's d_hyper."""
+    orc = _oracle()
+    ls, os_, noise, id_cov = hyper_values(b)
+    k0, k1 = orc.parse_kernel_lists(b.L, **b.lists, id_covariate=id_cov)
+    ls_p, os_p = [], []
+    i_ls = 0
+    for i_c, comp in enumerate(k0 + k1):
+        comp.outputscale = os_[i_c].to(device).clone().requires_grad_(requires_grad)
+        os_p.append(comp.outputscale)
+        for k in sorted(comp.lengthscales):
+            comp.lengthscales[k] = ls[i_ls].to(device).clone().requires_grad_(requires_grad)
+            ls_p.append(comp.lengthscales[k])
+            i_ls += 1
+    nz = noise.to(device).clone().requires_grad_(requires_grad)
+    return k0, k1, nz, ls_p + os_p + [nz]
+
+
+def oracle_step_fn(b, n_subjects, device="cpu"):
+    """One full step of the oracle port on the first n_subjects of b, taken as the whole data set (P_tot = P_batch =
+    n_subjects, so the minibatch scale is 1): fwd + backward + NG update.  Returns step() -> dict of outputs (kld, grad_m,
+    grad_H, d_mu, d_log_v, d_hyper [n_hyp, L])."""
+    orc = _oracle()
+    L = b.L
     rows = int(b.offsets[n_subjects])
+    P_tot = P_glob = n_subjects
+    N_tot = rows
+    dev = lambda t: t.to(device)
+    x, mu0, lv0, z = dev(b.x[:rows]), dev(b.mu[:rows]), dev(b.log_v[:rows]), dev(b.z)
+    k0, k1, noise, params = oracle_components(b, device)
+    ragged = isinstance(b.T, tuple)
+    state = {"m": dev(b.m).clone(), "H": dev(b.H).clone()}
+
+    def step(update=True):
+        mu = mu0.clone().requires_grad_(True)
+        lv = lv0.clone().requires_grad_(True)
+        if ragged:
+            kld, gm, gH = orc.kld_iter(k0, k1, noise, L, state["m"], state["H"], x, mu, lv, z, P_tot, P_glob, N_tot,
+                                       True, 2, EPS)
+        else:
+            kld, gm, gH = orc.kld_fixed_T(k0, k1, noise, L, state["m"], state["H"], x, mu, lv, z, P_tot, P_glob, int(b.T),
+                                          True, EPS)
+        kld.sum().backward()
+        out = dict(kld=kld.detach().sum(), grad_m=gm.detach(), grad_H=gH.detach(), d_mu=mu.grad, d_log_v=lv.grad,
+                   d_hyper=torch.stack([p_.grad for p_ in params]))
+        if update:
+            state["m"], state["H"] = orc.ng_step(state["m"], state["H"], gm.detach(), gH.detach(), LR)
+        out["m_new"], out["H_new"] = (state["m"], state["H"]) if update else (None, None)
+        for p_ in params:
+            p_.grad = None
+        return out
+    return step
+
+
+def reference_step_fn(b, n_subjects):
+    """The reference's OWN functions (byte-for-byte copies under baseline/_ref, oracle/install_ref.py) on the host CPU:
+    kernel_gen.generate_kernel_batched + elbo_functions.minibatch_KLD_upper_bound[_iter] + backward + the natural-gradient
+    update of training.py:129-135.  GPyTorch (absent third party) resolves to oracle/gpytorch_standin."""
+    import importlib.util
+    import warnings
+    warnings.filterwarnings("ignore")
+    orc = _oracle()
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "gpytorch_standin"))
+    import gpytorch
+    ref = {}
+    for name in ("kernel_spec", "kernel_gen", "elbo_functions"):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "baseline", "_ref", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        ref[name] = mod
+    L = b.L
+    ls, os_, noise, id_cov = hyper_values(b)
+    cm0, cm1 = ref["kernel_gen"].generate_kernel_batched(L, **b.lists, id_covariate=id_cov)
+    cm0.double(), cm1.double()
+    i_c = i_l = 0
+    for mod in (cm0, cm1):
+        for sk in mod.kernels:
+            sk.outputscale = os_[i_c].clone()
+            i_c += 1
+            for rb in [mm for mm in sk.modules() if isinstance(mm, gpytorch.kernels.RBFKernel)]:
+                rb.lengthscale = ls[i_l].clone().view(-1, 1, 1)
+                i_l += 1
+    lik = gpytorch.likelihoods.GaussianLikelihood(batch_shape=torch.Size([L]),
+                                                  noise_constraint=gpytorch.constraints.GreaterThan(1e-8)).double()
+    lik.noise = noise.view(L, 1)
+    rows = int(b.offsets[n_subjects])
+    P_tot = P_glob = n_subjects                 # the sample is the whole data set of the call (minibatch scale 1)
+    N_tot = rows
     x, mu0, lv0 = b.x[:rows], b.mu[:rows], b.log_v[:rows]
-    k0, k1 = orc.parse_kernel_lists(L, **b.lists, id_covariate=2)
-    params = []
-    for c in k0 + k1:
-        c.outputscale = c.outputscale.to(device).clone().requires_grad_(True)
-        params.append(c.outputscale)
-        for k in list(c.lengthscales):
-            c.lengthscales[k] = c.lengthscales[k].to(device).clone().requires_grad_(True)
-            params.append(c.lengthscales[k])
-    noise = torch.ones(L, dtype=torch.float64, device=device)
     ragged = isinstance(b.T, tuple)
     state = {"m": b.m.clone(), "H": b.H.clone()}
+    EFr = ref["elbo_functions"]
 
     def step():
         mu = mu0.clone().requires_grad_(True)
         lv = lv0.clone().requires_grad_(True)
         if ragged:
-            kld, gm, gH = orc.kld_iter(k0, k1, noise, L, state["m"], state["H"], x, mu, lv, b.z, b.P, n_subjects, b.N,
-                                       True, 2, 1e-6)
+            kld, gm, gH = EFr.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, state["m"], state["H"], x, mu, lv, b.z, P_tot,
+                                                             P_glob, N_tot, True, id_cov, EPS)
         else:
-            kld, gm, gH = orc.kld_fixed_T(k0, k1, noise, L, state["m"], state["H"], x, mu, lv, b.z, b.P, n_subjects, b.T,
-                                          True, 1e-6)
+            kld, gm, gH = EFr.minibatch_KLD_upper_bound(cm0, cm1, lik, L, state["m"], state["H"], x, mu, lv, b.z, P_tot,
+                                                        P_glob, int(b.T), True, EPS)
         kld.sum().backward()
-        m1, H1 = orc.ng_step(state["m"], state["H"], gm.detach(), gH.detach(), 1e-3)
-        for p_ in params:
-            p_.grad = None
-        return float(kld.detach().sum())
+        state["m"], state["H"] = orc.ng_step(state["m"], state["H"], gm.detach(), gH.detach(), LR)   # training.py:129-135
+        for mod in (cm0, cm1, lik):
+            mod.zero_grad(set_to_none=True)
+        return dict(kld=kld.detach().sum())
     return step
 
 
+def time_cpu(b, n_subjects, steps, warmup, prefer_ref=True):
+    """CPU arm: the reference's own modules when baseline/_ref holds them, else the oracle port; all host threads."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    kind = "port"
+    step = None
+    if prefer_ref and all(os.path.exists(os.path.join(ROOT, "baseline", "_ref", f)) for f in
+                          ("elbo_functions.py", "kernel_gen.py", "kernel_spec.py")):
+        try:
+            step = reference_step_fn(b, n_subjects)
+            kind = "reference"
+        except Exception as ex:                       # e.g. a torch API the reference needs is gone: say so, use the port
+            print(f"bench: baseline/_ref could not be driven ({repr(ex)[:200]}); using the oracle port", file=sys.stderr)
+    if step is None:
+        step = oracle_step_fn(b, n_subjects)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_subjects / dt, dt, kind
+
+
+def default_cpu_subjects(args, b, spb):
+    if args.cpu_subjects is not None:
+        return min(args.cpu_subjects, spb)
+    return spb if (not isinstance(b.T, tuple) and b.M <= 64 and spb <= 1000) else min(100, spb)
+
+
 def time_gpu_reference(b, device, steps=3, warmup=2):
-    """The same oracle port of the reference, run with stock PyTorch CUDA ops (ATen / cuBLAS / cuSOLVER) on this GPU: the
-    "existing GPU path" (SURVEY 8d).  All subjects of the minibatch, fwd + backward + NG update."""
-    import copy
-    bg = copy.copy(b)
-    for k in ("x", "mu", "log_v", "z", "m", "H"):
-        setattr(bg, k, getattr(b, k).to(device))
+    """The oracle port of the reference with stock PyTorch CUDA ops (ATen / cuBLAS / cuSOLVER) on this GPU: the "existing
+    GPU path" (SURVEY 8d).  All subjects of the rank's minibatch, fwd + backward + NG update."""
     with torch.device(device):
-        step = cpu_reference_step_fn(bg, b.P, device=device)
+        step = oracle_step_fn(b, b.P, device=device)
         for _ in range(warmup):
             step()
         torch.cuda.synchronize(device)
@@ -195,16 +349,9 @@ def time_gpu_reference(b, device, steps=3, warmup=2):
     return b.P / (ms * 1e-3), ms
 
 
-def time_cpu(b, n_subjects, steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_reference_step_fn(b, n_subjects)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return n_subjects / dt, dt
+def rel_err(a, ref):
+    a, ref = a.detach().double().reshape(-1), ref.detach().double().reshape(-1).to(a.device)
+    return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-300))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -227,134 +374,146 @@ def emit(line):
     out.flush()
 
 
-def main():
-    args = parse()
-    _quiet_stdout()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = args.cfg
+# ---------------------------------------------------------------------------------------------------------------
+# one configuration on this rank's GPU
+# ---------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        from lvae_b200 import synth
-        b = synth.make_batch(cfg, P=args.spb, L=args.L, M=args.M)
-        n_sub = min(args.cpu_subjects, args.spb)
-        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-        val, dt = time_cpu(b, n_sub, steps, warm)
-        cores = os.cpu_count() or 1
-        sample = (f"{n_sub} of the {args.spb} subjects of one minibatch per step (fwd + backward + NG update), "
-                  f"{steps} steps after {warm} warm-up, torch CPU FP64 with {cores} threads")
-        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "impl": "reference",
-                "config": {"workload": f"{cfg}: Health-MNIST-shaped synthetic, {args.spb} subjects x T={b.T}, L={b.L}, "
-                                       f"M={b.M}, additive kernel {len(b.lists['cat_int_kernel']) + len(b.lists['cat_kernel']) + len(b.lists['sqexp_kernel']) + len(b.lists['bin_kernel'])} components"},
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        emit(line)
-        return 0
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
-    from lvae_b200 import _lib, ops, synth
-    import lvae_b200.elbo_functions as EF
-    from lvae_b200.training import natural_gradient_step
+def build_modules(b, device):
+    """Drop-in kernel modules + likelihood of this package with the problem's hyper-parameters."""
+    from lvae_b200.constraints import GreaterThan
+    from lvae_b200.gp_kernels import RBFKernel
     from lvae_b200.kernel_gen import generate_kernel_batched
     from lvae_b200.likelihoods import GaussianLikelihood
-    from lvae_b200.constraints import GreaterThan
+    ls, os_, noise, id_cov = hyper_values(b)
+    L = b.L
+    cm0, cm1 = generate_kernel_batched(L, **b.lists, id_covariate=id_cov)
+    cm0, cm1 = cm0.double().to(device), cm1.double().to(device)
+    i_c = i_l = 0
+    for mod in (cm0, cm1):
+        for sk in mod.kernels:
+            sk.outputscale = os_[i_c]
+            i_c += 1
+            for rb in [mm for mm in sk.modules() if isinstance(mm, RBFKernel)]:
+                rb.lengthscale = ls[i_l].view(L, 1, 1)
+                i_l += 1
+    lik = GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=GreaterThan(1e-8)).double().to(device)
+    lik.noise = noise.view(L, 1)
+    return cm0, cm1, lik
+
+
+def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup, strong=False, headline=False, L=None,
+               M=None, parity_only=False):
+    """Time one configuration (device-resident + end to end), check parity on the timed problem; returns rank 0's dict."""
+    from lvae_b200 import _lib, ops
+    import lvae_b200.elbo_functions as EF
     from lvae_b200.spec import build_structure, flatten
+    from lvae_b200.training import natural_gradient_step
     lib = _lib.load()
     EF.set_kernel_path(args.path)
-
-    b = make_problem(cfg, args.spb, rank, world, args.L, args.M)
-    L, M, Q, P_b, N_b = b.L, b.M, b.x.shape[1], args.spb, b.N
-    P_tot = P_b * world
-    Tl = np.diff(b.offsets)
+    if strong:                                   # fixed global minibatch of `spb` subjects split over the ranks
+        from lvae_b200 import distributed as D
+        bg = make_problem(cfg, spb, 0, 1, L, M)
+        p_lo, p_hi = D.shard_subjects(bg.offsets, rank, world)
+        r_lo, r_hi = int(bg.offsets[p_lo]), int(bg.offsets[p_hi])
+        import copy
+        b = copy.copy(bg)
+        b.x, b.mu, b.log_v = bg.x[r_lo:r_hi], bg.mu[r_lo:r_hi], bg.log_v[r_lo:r_hi]
+        b.offsets = bg.offsets[p_lo:p_hi + 1] - bg.offsets[p_lo]
+        b.P = p_hi - p_lo
+        P_b, P_glob = b.P, spb
+    else:
+        b = make_problem(cfg, spb, rank, world, L, M)
+        P_b, P_glob = spb, spb * world
+    L, M, Q, N_b = b.L, b.M, b.x.shape[1], b.N
     ragged = isinstance(b.T, tuple)
-    cm0, cm1 = generate_kernel_batched(L, **b.lists, id_covariate=2)
-    cm0, cm1 = cm0.double().to(device), cm1.double().to(device)
-    lik = GaussianLikelihood(batch_shape=torch.Size([L]), noise_constraint=GreaterThan(1e-8)).double().to(device)
-    lik.noise = 1.0
+    Tl = np.diff(b.offsets)
+    N_glob = N_b
+    if dist is not None:
+        t = torch.tensor([N_b], dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        N_glob = int(t.item())
+    P_tot = P_glob                                # the data set is the (global) minibatch: P_tot / P_batch = 1
+    N_tot = N_glob
+    cm0, cm1, lik = build_modules(b, device)
     st, ls, os_ = build_structure(flatten(cm0), flatten(cm1), L, device=device)
     ls, os_ = ls.detach(), os_.detach()
-    noise = torch.ones(L, dtype=torch.float64, device=device)
+    noise = lik.noise.detach().reshape(L).contiguous()
     dev = lambda t: t.to(device)
     x, mu, lv, z = dev(b.x), dev(b.mu), dev(b.log_v), dev(b.z)
     m, H = dev(b.m).clone(), dev(b.H).clone()
     offsets = torch.from_numpy(b.offsets).to(torch.int32).to(device)
     T_max, sum_T2 = int(Tl.max()), int((Tl * Tl).sum())
-    const = L * (N_b * world) / 2 if ragged else L * P_tot * int(b.T) / 2
-    call = (ops.make_kld_call(st, L, M, Q, Tl, device, natural_gradient=True, path=args.path) if ragged else
-            ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path))
-    is_split = isinstance(call, ops.SplitKldCall)
+    const = L * N_tot / 2 if ragged else L * P_tot * int(b.T) / 2
+    scale = P_tot / P_glob
+
+    def new_call(group_unused=None):
+        return (ops.make_kld_call(st, L, M, Q, Tl, device, natural_gradient=True, path=args.path) if ragged else
+                ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path))
+    call = new_call()
     ng_ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=torch.float64, device=device)
     ng_info = torch.zeros(4, dtype=torch.int32, device=device)
-    lr = 1e-3
+    group = dist.group.WORLD if dist is not None else None
 
-    exchange_note = None
-    if dist is not None and args.exchange == "p2p":       # all ranks agree on the exchange path before any timed work
-        ok = 1
-        try:
-            from lvae_b200 import distributed as D
-            D.peer_stats(dist.group.WORLD, call.stats.numel(), device)
-        except Exception as ex:
-            ok, exchange_note = 0, f"symmetric memory unavailable ({repr(ex)[:120]}): NCCL all-reduce"
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            args.exchange = "nccl"
-            exchange_note = exchange_note or "a peer could not map symmetric memory: NCCL all-reduce"
+    hold = {"call": call}
 
-    def device_step():
-        call.bind(x, offsets, mu, lv, z, m.view(L, M), H, ls, os_, noise, P_tot / (P_b * world), const, 1e-6)
-        call.head()
-        EF.exchange_stats(call, dist.group.WORLD if dist is not None else None, args.exchange)
-        call.tail()
-        rc = lib.lvae_ng_step_f64(_lib.ptr(m), _lib.ptr(H), _lib.ptr(call.grad_m), _lib.ptr(call.grad_H),
-                                  _lib.ptr(call.Hinv), lr, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
-                                  _lib.stream_ptr(device))
-        _lib.check(rc, "lvae_ng_step_f64")
+    def device_step(c=None, mm=None, HH=None, grp=group, update=True, sc=None, ct=None):
+        c = hold["call"] if c is None else c
+        mm = m if mm is None else mm
+        HH = H if HH is None else HH
+        c.bind(x, offsets, mu, lv, z, mm.view(L, M), HH, ls, os_, noise, scale if sc is None else sc,
+               const if ct is None else ct, EPS)
+        c.head()
+        EF.exchange_stats(c, grp, args.exchange)
+        c.tail()
+        if update:
+            rc = lib.lvae_ng_step_f64(_lib.ptr(mm), _lib.ptr(HH), _lib.ptr(c.grad_m), _lib.ptr(c.grad_H),
+                                      _lib.ptr(c.Hinv), LR, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
+                                      _lib.stream_ptr(device))
+            _lib.check(rc, "lvae_ng_step_f64")
 
-    if args.path == 1:
-        kernel_path = "generic"
-    elif M <= 64:
-        kernel_path = ("fused (one DMMA kernel per subject pass)" if T_max <= 24 or args.path == 2 else
-                       "split: subjects with T <= 24 fused v2 + prep v3, longer ones fused v1 + 4-warp prep" if
-                       is_split else "fused v1")
-    else:
-        kernel_path = "gemm (U/V materialised, S = U^T U and Y = V W as batched DMMA GEMMs)" if T_max <= 24 else "generic"
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)   # > 126 MB L2
     fl = algorithmic_flops(Tl, L, M, st.n_comp0, st.n_comp1, P_b)
-    peak = dgemm_peak_tflops(device) if rank == 0 else None
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- parity on the timed problem (before the timing loops touch m, H) ----------------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = check_parity(args, b, call, device_step, m, H, device, dist, rank, world, P_tot, P_glob, N_tot,
+                              dict(x=x, mu=mu, lv=lv, offsets_np=b.offsets, z=z, ls=ls, os=os_, noise=noise, st=st,
+                                   scale=scale, const=const, ragged=ragged, T=b.T), max_over_ranks)
+
+    if parity_only:                                # the -m gpu full-size parity tests stop here
+        res = Ctx()
+        res.out = {"parity": parity}
+        return res
+
     # ---- device-resident timing -------------------------------------------------------------------------------
     m0, H0 = m.clone(), H.clone()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         device_step()
     barrier()
     lib.lvae_profile_enable(1)
     launches0 = ops.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    phase_ms = np.zeros((args.steps, 6))
-    clocks = ClockSampler(local_rank)
-    if rank == 0:                                  # rank 0's GPU, sampled through the device-timed AND the end-to-end timed regions
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    phase_ms = np.zeros((steps, 6))
+    clocks = ClockSampler(device.index)
+    if rank == 0 and headline:                     # rank 0's GPU, sampled through the device-timed AND the end-to-end timed regions
         clocks.__enter__()
     barrier()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(1.0)                           # L2 flush between timed steps (outside the event pair)
         ev[i][0].record()
         device_step()
@@ -366,15 +525,13 @@ def main():
     lib.lvae_profile_enable(0)
     total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
     call.raise_on_info()
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = P_b * world / (ms_per_step * 1e-3)
+    ms_per_step = max_over_ranks(total_ms) / steps
+    value = P_glob / (ms_per_step * 1e-3)
     finite = bool(torch.isfinite(call.kld_per_latent).all() and torch.isfinite(H).all())
+    is_split = isinstance(call, ops.SplitKldCall)
 
     # ---- end to end through the public API with host buffers --------------------------------------------------
+    hold["call"] = None
     del call                                   # its workspace (tens of GB at M > 64 with large minibatches) is not needed any more
     torch.cuda.empty_cache()
     m.copy_(m0); H.copy_(H0)
@@ -405,6 +562,16 @@ def main():
             d["lv"].copy_(hlv, non_blocking=True)
             d["ready"].record(s_in)
 
+    def api_step(xd, mud, lvd):
+        if ragged:
+            kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, state["m"], state["H"], xd, mud, lvd, z,
+                                                            P_tot, P_glob, N_tot, True, 2, EPS)
+        else:
+            kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, state["m"], state["H"], xd, mud, lvd, z, P_tot,
+                                                       P_glob, int(b.T), True, EPS)
+        kld.sum().backward()
+        return kld, gm, gH
+
     def e2e_step(i):
         d = dbuf[i % 2]
         prefetch(i + 1)
@@ -412,15 +579,9 @@ def main():
         xd = d["x"]
         mud = d["mu"].detach().requires_grad_(True)
         lvd = d["lv"].detach().requires_grad_(True)
-        if ragged:
-            kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, state["m"], state["H"], xd, mud, lvd, z,
-                                                            P_tot, P_b * world, N_b * world, True, 2, 1e-6)
-        else:
-            kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, state["m"], state["H"], xd, mud, lvd, z, P_tot,
-                                                       P_b * world, int(b.T), True, 1e-6)
-        kld.sum().backward()
+        kld, gm, gH = api_step(xd, mud, lvd)
         d["free"].record(main)
-        state["m"], state["H"] = natural_gradient_step(state["m"], state["H"], gm, gH, lr)
+        state["m"], state["H"] = natural_gradient_step(state["m"], state["H"], gm, gH, LR)
         done = torch.cuda.Event()
         done.record(main)
         gmu, glv, kd = mud.grad, lvd.grad, kld.detach().reshape(1)
@@ -432,205 +593,466 @@ def main():
             for t_ in (gmu, glv, kd):
                 t_.record_stream(s_out)
             out_done.record(s_out)
-        cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True)
+        cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
 
     for d in dbuf:
         d["free"].record(main)
     n_e2e = 0
     prefetch(0)
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         e2e_step(n_e2e); n_e2e += 1
     main.wait_event(out_done)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step(n_e2e); n_e2e += 1
     main.wait_event(out_done)                              # the last step's results have reached host memory
     e1.record()
     barrier()
-    if rank == 0:
-        clocks.__exit__(None, None, None)
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / args.steps
-    e2e_val = P_b * world / (e2e_ms * 1e-3)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    e2e_val = P_glob / (e2e_ms * 1e-3)
     h2d = (hx.numel() + hmu.numel() + hlv.numel()) * 8
     d2h = (out_mu.numel() + out_lv.numel() + 1) * 8
     EF.check_errors()
+
+    # the plain loop a user writes first: immediate error check (one device sync per call, like torch.cholesky), copies on the
+    # compute stream, nothing overlapped
     EF.set_error_check("immediate")
+    state["m"], state["H"] = m0.clone(), H0.clone()
+
+    def plain_step():
+        xd = hx.to(device, non_blocking=True)
+        mud = hmu.to(device, non_blocking=True).requires_grad_(True)
+        lvd = hlv.to(device, non_blocking=True).requires_grad_(True)
+        kld, gm, gH = api_step(xd, mud, lvd)
+        state["m"], state["H"] = natural_gradient_step(state["m"], state["H"], gm, gH, LR)
+        out_mu.copy_(mud.grad, non_blocking=True)
+        out_lv.copy_(lvd.grad, non_blocking=True)
+        out_kld.copy_(kld.detach().reshape(1), non_blocking=True)
+        cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
+    for _ in range(3):
+        plain_step()
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        plain_step()
+    e1.record()
+    barrier()
+    plain_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    if rank == 0 and headline:
+        clocks.__exit__(None, None, None)
     EF.set_process_group(None)
 
-    lat = None
-    if not args.no_latency_point and rank == 0 and world == 1 and P_b >= 20:
-        spb2 = 20
-        rows = int(b.offsets[spb2])
-        off2 = offsets[:spb2 + 1].contiguous()
-        c2 = ops.KldCall(st, L, M, Q, spb2, rows, T_max, int((Tl[:spb2] ** 2).sum()), device, True, args.path)
-        mm, HH = m0.clone(), H0.clone()
+    if M <= 64:
+        kernel_path = ("generic" if args.path == 1 else
+                       "split: subjects with T <= 24 fused v2 + prep v3, longer ones fused v1 + 4-warp prep" if is_split else
+                       "fused (one DMMA kernel per subject pass)")
+    else:
+        kernel_path = "gemm (U/V materialised, S = U^T U and Y = V W as batched DMMA GEMMs)" if T_max <= 24 else "generic"
+    subj_ms = float(phase_ms[:, 2].mean())
+    achieved = fl["subjects"] / (subj_ms * 1e-3) * 1e-12 if subj_ms > 0 else None
+    res = Ctx()
+    res.b, res.st, res.x, res.mu, res.lv, res.z, res.offsets = b, st, x, mu, lv, z, offsets
+    res.ls, res.os, res.noise, res.m0, res.H0, res.cm0, res.cm1, res.lik = ls, os_, noise, m0, H0, cm0, cm1, lik
+    res.P_tot, res.N_tot, res.const, res.Tl, res.T_max = P_tot, N_tot, const, Tl, T_max
+    res.out = {
+        "value": value, "ms_per_step": ms_per_step, "subjects_per_gpu": P_b, "global_batch_subjects": P_glob,
+        "scaling": "strong" if strong else "weak",
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "plain_loop_value": P_glob / (plain_ms * 1e-3), "plain_loop_ms_per_step": plain_ms,
+                "how": "public API (minibatch_KLD_upper_bound[_iter] + backward + natural_gradient_step); every step copies "
+                       "x, mu, log_v from pinned host memory and returns kld, d_mu, d_log_v to pinned host memory.  `value`: "
+                       "the copies of neighbouring steps overlap the compute on two copy streams and the Cholesky-failure "
+                       "flags are checked deferred; `plain_loop_value`: same API in a plain loop (copies on the compute "
+                       "stream, one device sync per call for the error check, as torch.cholesky has)"},
+        "gpu_launches": int(launches), "finite": finite, "parity": parity, "kernel_path": kernel_path,
+        "phase_ms": {n: float(phase_ms[:, i].mean()) for i, n in
+                     enumerate(["head", "prep", "subjects", "reduce", "tail", "ng_step"])},
+        "roofline_frac": (achieved / peak) if (achieved and peak) else None,
+        "subject_pass_tflops": achieved, "step_tflops": fl["step"] / (ms_per_step * 1e-3) * 1e-12,
+        "flops": fl, "clocks": clocks.summary() if (rank == 0 and headline) else None,
+    }
+    return res
 
-        def small():
-            c2.bind(x[:rows], off2, mu[:rows], lv[:rows], z, mm.view(L, M), HH, ls, os_, noise, P_tot / spb2, const, 1e-6)
-            c2.run()
-            lib.lvae_ng_step_f64(_lib.ptr(mm), _lib.ptr(HH), _lib.ptr(c2.grad_m), _lib.ptr(c2.grad_H),
-                                 _lib.ptr(c2.Hinv), lr, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
-                                 _lib.stream_ptr(device))
+
+def check_parity(args, b, call, device_step, m, H, device, dist, rank, world, P_tot, P_glob, N_tot, t, max_over_ranks):
+    """Parity on the timed problem.  (a) This rank's shard, CUDA path on one GPU (no exchange) vs the oracle port run with
+    stock torch ops on the same GPU, global scaling constants: kld, grad_m, grad_H, d_mu, d_log_v, hyper-gradient vector,
+    and (m, H) after the natural-gradient update.  (b) N > 1: the sharded result vs a one-GPU CUDA evaluation of the
+    gathered minibatch on every rank (kld, grad_m, grad_H, hyper-gradients, own rows of d_mu / d_log_v)."""
+    from lvae_b200 import _lib, ops
+    lib = _lib.load()
+    L, M = b.L, b.M
+    mm, HH = m.clone(), H.clone()
+    ragged = t["ragged"]
+    const_loc = L * int(t["x"].shape[0]) / 2 if ragged else L * int(b.P) * int(b.T) / 2
+    # this rank's shard as a data set of its own (scale 1, its own constant term), incl. the NG update of the copies
+    device_step(c=call, mm=mm, HH=HH, grp=None, update=True, sc=1.0, ct=const_loc)
+    torch.cuda.synchronize(device)
+    call.raise_on_info()
+    ours = dict(kld=call.kld_per_latent.sum(), grad_m=call.grad_m.clone(), grad_H=call.grad_H.clone(),
+                d_mu=call.d_mu.clone(), d_log_v=call.d_log_v.clone(), d_hyper=call.d_hyper.clone(), m_new=mm, H_new=HH)
+    with torch.device(device):
+        ref = oracle_step_fn(b, b.P, device=device)(update=True)
+    torch.cuda.synchronize(device)
+    errs = {k: rel_err(ours[k], ref[k]) for k in ("kld", "grad_m", "grad_H", "d_mu", "d_log_v", "d_hyper", "m_new", "H_new")}
+    dh, rh = ours["d_hyper"].double(), ref["d_hyper"].double().to(device)
+    worst_entry = float(((dh - rh).abs() / rh.abs().clamp_min(1e-300)).max())
+    max_rel = max(errs.values())
+    max_rel_all = max_over_ranks(max_rel)
+    out = {"max_rel": max_rel_all, "tol": TOL, "ok": bool(max_rel_all <= TOL),
+           "per_tensor_rank0": errs, "d_hyper_worst_single_entry_rel_rank0": worst_entry,
+           "against": "oracle port of the reference (oracle/lvae_oracle.py) with stock torch CUDA ops on this GPU, same inputs "
+                      "as the timed step (this rank's subjects), max-norm relative error per tensor",
+           "n_subjects_checked_per_rank": int(b.P)}
+    del ref
+    torch.cuda.empty_cache()
+    if dist is not None:                                   # (b) cross-rank: sharded vs one-GPU evaluation of the gathered batch
+        m2, H2 = m.clone(), H.clone()
+        device_step(c=call, mm=m2, HH=H2, grp=dist.group.WORLD, update=True)
+        torch.cuda.synchronize(device)
+        sh = dict(kld=call.kld_per_latent.sum().clone(), grad_m=call.grad_m.clone(), grad_H=call.grad_H.clone(),
+                  d_mu=call.d_mu.clone(), d_log_v=call.d_log_v.clone(), d_hyper=call.d_hyper.clone(), m_new=m2, H_new=H2)
+        nrows = torch.tensor([t["x"].shape[0]], dtype=torch.int64, device=device)
+        allrows = [torch.zeros_like(nrows) for _ in range(world)]
+        dist.all_gather(allrows, nrows)
+        allrows = [int(v.item()) for v in allrows]
+        nsub = torch.tensor([b.P], dtype=torch.int64, device=device)
+        allsub = [torch.zeros_like(nsub) for _ in range(world)]
+        dist.all_gather(allsub, nsub)
+        allsub = [int(v.item()) for v in allsub]
+
+        def gather_rows(v):
+            parts = [torch.empty(n, *v.shape[1:], dtype=v.dtype, device=device) for n in allrows]
+            dist.all_gather(parts, v.contiguous())
+            return torch.cat(parts)
+        gx, gmu, glv = gather_rows(t["x"]), gather_rows(t["mu"]), gather_rows(t["lv"])
+        counts = [torch.empty(n, dtype=torch.int64, device=device) for n in allsub]
+        dist.all_gather(counts, torch.from_numpy(np.diff(t["offsets_np"]).astype(np.int64)).to(device))
+        Tg = torch.cat(counts).cpu().numpy()
+        offg = torch.from_numpy(np.concatenate([[0], np.cumsum(Tg)]).astype(np.int32)).to(device)
+        Q = gx.shape[1]
+        big = (ops.make_kld_call(t["st"], L, M, Q, Tg, device, natural_gradient=True, path=args.path) if t["ragged"] else
+               ops.KldCall(t["st"], L, M, Q, len(Tg), int(gx.shape[0]), int(Tg.max()), int((Tg * Tg).sum()), device,
+                           natural_gradient=True, path=args.path))
+        m3, H3 = m.clone(), H.clone()
+        big.bind(gx, offg, gmu, glv, t["z"], m3.view(L, M), H3, t["ls"], t["os"], t["noise"], t["scale"], t["const"], EPS)
+        big.run()
+        ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=torch.float64, device=device)
+        info = torch.zeros(4, dtype=torch.int32, device=device)
+        _lib.check(lib.lvae_ng_step_f64(_lib.ptr(m3), _lib.ptr(H3), _lib.ptr(big.grad_m), _lib.ptr(big.grad_H),
+                                        _lib.ptr(big.Hinv), LR, L, M, _lib.ptr(ws), _lib.ptr(info),
+                                        _lib.stream_ptr(device)), "lvae_ng_step_f64")
+        torch.cuda.synchronize(device)
+        big.raise_on_info()
+        r0 = sum(allrows[:rank])
+        one = dict(kld=big.kld_per_latent.sum(), grad_m=big.grad_m, grad_H=big.grad_H,
+                   d_mu=big.d_mu[r0:r0 + allrows[rank]], d_log_v=big.d_log_v[r0:r0 + allrows[rank]], d_hyper=big.d_hyper,
+                   m_new=m3, H_new=H3)
+        cerr = {k: rel_err(sh[k], one[k]) for k in one}
+        cmax = max_over_ranks(max(cerr.values()))
+        ident = torch.stack([sh["kld"].reshape(()), sh["grad_H"].sum(), sh["d_hyper"].sum()])
+        lo, hi = ident.clone(), ident.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["cross_rank"] = {"max_rel": cmax, "tol": TOL, "ok": bool(cmax <= TOL), "per_tensor_rank0": cerr,
+                             "ranks_bit_identical": bool(torch.equal(lo, hi)),
+                             "against": f"one-GPU CUDA evaluation of the gathered {int(len(Tg))}-subject minibatch on every rank"}
+        out["ok"] = bool(out["ok"] and out["cross_rank"]["ok"])
+        del big
+        torch.cuda.empty_cache()
+    return out
+
+
+def latency_point(args, R, device):
+    """spb = 20, the reference's default batch (launch / latency regime)."""
+    from lvae_b200 import _lib, ops
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200.training import natural_gradient_step
+    lib = _lib.load()
+    b, st = R.b, R.st
+    L, M, Q = b.L, b.M, R.x.shape[1]
+    ragged = isinstance(b.T, tuple)
+    spb2 = 20
+    rows = int(b.offsets[spb2])
+    off2 = R.offsets[:spb2 + 1].contiguous()
+    c2 = ops.KldCall(st, L, M, Q, spb2, rows, R.T_max, int((R.Tl[:spb2] ** 2).sum()), device, True, args.path)
+    mm, HH = R.m0.clone(), R.H0.clone()
+    ng_ws = torch.empty(int(lib.lvae_ng_workspace_doubles(L, M)), dtype=torch.float64, device=device)
+    ng_info = torch.zeros(4, dtype=torch.int32, device=device)
+    x, mu, lv, z = R.x, R.mu, R.lv, R.z
+
+    def small():
+        c2.bind(x[:rows], off2, mu[:rows], lv[:rows], z, mm.view(L, M), HH, R.ls, R.os, R.noise, R.P_tot / spb2, R.const, EPS)
+        c2.run()
+        lib.lvae_ng_step_f64(_lib.ptr(mm), _lib.ptr(HH), _lib.ptr(c2.grad_m), _lib.ptr(c2.grad_H),
+                             _lib.ptr(c2.Hinv), LR, L, M, _lib.ptr(ng_ws), _lib.ptr(ng_info),
+                             _lib.stream_ptr(device))
+    for _ in range(5):
+        small()
+    torch.cuda.synchronize()
+    a_, b__ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_.record()
+    for _ in range(50):
+        small()
+    b__.record(); torch.cuda.synchronize()
+    lat = {"spb": spb2, "ms_per_step": a_.elapsed_time(b__) / 50, "subjects_per_s": spb2 / (a_.elapsed_time(b__) / 50 * 1e-3),
+           "what": "spb = 20 (the reference's default minibatch), device-resident inputs, bound + gradients + NG update"}
+    cm0, cm1, lik = R.cm0, R.cm1, R.lik
+    try:      # the same small minibatch through the public API with pinned host inputs (Python + launch overhead regime)
+        hx2, hmu2, hlv2 = b.x[:rows].pin_memory(), b.mu[:rows].pin_memory(), b.log_v[:rows].pin_memory()
+        st2 = {"m": R.m0.clone(), "H": R.H0.clone()}
+        o_mu = torch.empty_like(b.mu[:rows]).pin_memory()
+
+        def small_api():
+            xd = hx2.to(device, non_blocking=True)
+            mud = hmu2.to(device, non_blocking=True).requires_grad_(True)
+            lvd = hlv2.to(device, non_blocking=True).requires_grad_(True)
+            if ragged:
+                kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, st2["m"], st2["H"], xd, mud, lvd, z, R.P_tot,
+                                                                spb2, R.N_tot, True, 2, EPS)
+            else:
+                kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, st2["m"], st2["H"], xd, mud, lvd, z, R.P_tot, spb2,
+                                                           int(b.T), True, EPS)
+            kld.sum().backward()
+            st2["m"], st2["H"] = natural_gradient_step(st2["m"], st2["H"], gm, gH, LR)
+            o_mu.copy_(mud.grad, non_blocking=True)
+            cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
+        EF.set_error_check("deferred")
         for _ in range(5):
-            small()
+            small_api()
         torch.cuda.synchronize()
-        a_, b__ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
+        t0 = time.perf_counter()
         for _ in range(50):
-            small()
-        b__.record(); torch.cuda.synchronize()
-        lat = {"spb": spb2, "ms_per_step": a_.elapsed_time(b__) / 50, "subjects_per_s": spb2 / (a_.elapsed_time(b__) / 50 * 1e-3),
-               "what": "spb = 20 (the reference's default minibatch), device-resident inputs, bound + gradients + NG update"}
-        try:      # the same small minibatch through the public API with pinned host inputs (Python + launch overhead regime)
-            hx2, hmu2, hlv2 = b.x[:rows].pin_memory(), b.mu[:rows].pin_memory(), b.log_v[:rows].pin_memory()
-            st2 = {"m": m0.clone(), "H": H0.clone()}
-            o_mu = torch.empty_like(b.mu[:rows]).pin_memory()
+            small_api()
+        torch.cuda.synchronize()
+        lat["e2e_ms_per_step"] = (time.perf_counter() - t0) / 50 * 1e3
+        lat["e2e_subjects_per_s"] = spb2 / (lat["e2e_ms_per_step"] * 1e-3)
+        EF.check_errors()
+        EF.set_error_check("immediate")
+    except Exception as ex:
+        lat["e2e_unavailable"] = repr(ex)[:160]
+    if not ragged:
+        try:  # public API again, but the GP side of the step is ONE graph replay (lvae_b200.graphed.GraphedHensmanStep)
+            from lvae_b200.graphed import GraphedHensmanStep
+            mg, Hg = R.m0.clone().reshape(L, M, 1).contiguous(), R.H0.clone().contiguous()
+            gstep = GraphedHensmanStep(cm0, cm1, lik, L, mg, Hg, z, R.P_tot, spb2, int(b.T), EPS, LR)
 
-            def small_api():
+            def small_graphed():
                 xd = hx2.to(device, non_blocking=True)
                 mud = hmu2.to(device, non_blocking=True).requires_grad_(True)
                 lvd = hlv2.to(device, non_blocking=True).requires_grad_(True)
-                if ragged:
-                    kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, st2["m"], st2["H"], xd, mud, lvd, z, P_tot,
-                                                                    spb2, N_b, True, 2, 1e-6)
-                else:
-                    kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, st2["m"], st2["H"], xd, mud, lvd, z, P_tot, spb2,
-                                                               int(b.T), True, 1e-6)
-                kld.sum().backward()
-                st2["m"], st2["H"] = natural_gradient_step(st2["m"], st2["H"], gm, gH, lr)
+                gstep(xd, mud, lvd).backward()
                 o_mu.copy_(mud.grad, non_blocking=True)
-                cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True)
-            EF.set_error_check("deferred")
+                cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
             for _ in range(5):
-                small_api()
+                small_graphed()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(50):
-                small_api()
+                small_graphed()
             torch.cuda.synchronize()
-            lat["e2e_ms_per_step"] = (time.perf_counter() - t0) / 50 * 1e3
-            lat["e2e_subjects_per_s"] = spb2 / (lat["e2e_ms_per_step"] * 1e-3)
-            EF.check_errors()
-            EF.set_error_check("immediate")
+            lat["graphed_api_ms_per_step"] = (time.perf_counter() - t0) / 50 * 1e3
+            lat["graphed_api_subjects_per_s"] = spb2 / (lat["graphed_api_ms_per_step"] * 1e-3)
+            gstep.check_errors()
+            lat["graphed_api_finite"] = bool(torch.isfinite(Hg).all())
         except Exception as ex:
-            lat["e2e_unavailable"] = repr(ex)[:160]
-        if not ragged:
-            try:  # public API again, but the GP side of the step is ONE graph replay (lvae_b200.graphed.GraphedHensmanStep)
-                from lvae_b200.graphed import GraphedHensmanStep
-                mg, Hg = m0.clone().reshape(L, M, 1).contiguous(), H0.clone().contiguous()
-                gstep = GraphedHensmanStep(cm0, cm1, lik, L, mg, Hg, z, P_tot, spb2, int(b.T), 1e-6, lr)
+            lat["graphed_api_unavailable"] = repr(ex)[:200]
+    try:      # the same step captured once into a CUDA graph (the C ABI is stream-ordered and capture-safe) and replayed
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            small()
+        torch.cuda.current_stream(device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            small()
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+        a_.record()
+        for _ in range(50):
+            graph.replay()
+        b__.record(); torch.cuda.synchronize()
+        lat["graph_ms_per_step"] = a_.elapsed_time(b__) / 50
+        lat["graph_subjects_per_s"] = spb2 / (a_.elapsed_time(b__) / 50 * 1e-3)
+        lat["graph_finite"] = bool(torch.isfinite(HH).all())
+    except Exception as ex:
+        lat["graph_unavailable"] = repr(ex)[:160]
+    return lat
 
-                def small_graphed():
-                    xd = hx2.to(device, non_blocking=True)
-                    mud = hmu2.to(device, non_blocking=True).requires_grad_(True)
-                    lvd = hlv2.to(device, non_blocking=True).requires_grad_(True)
-                    gstep(xd, mud, lvd).backward()
-                    o_mu.copy_(mud.grad, non_blocking=True)
-                    cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True)
-                for _ in range(5):
-                    small_graphed()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(50):
-                    small_graphed()
-                torch.cuda.synchronize()
-                lat["graphed_api_ms_per_step"] = (time.perf_counter() - t0) / 50 * 1e3
-                lat["graphed_api_subjects_per_s"] = spb2 / (lat["graphed_api_ms_per_step"] * 1e-3)
-                gstep.check_errors()
-                lat["graphed_api_finite"] = bool(torch.isfinite(Hg).all())
-            except Exception as ex:
-                lat["graphed_api_unavailable"] = repr(ex)[:200]
-        try:      # the same step captured once into a CUDA graph (the C ABI is stream-ordered and capture-safe) and replayed
-            side = torch.cuda.Stream(device)
-            side.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(side):
-                small()
-            torch.cuda.current_stream(device).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                small()
-            for _ in range(5):
-                graph.replay()
-            torch.cuda.synchronize()
-            a_.record()
-            for _ in range(50):
-                graph.replay()
-            b__.record(); torch.cuda.synchronize()
-            lat["graph_ms_per_step"] = a_.elapsed_time(b__) / 50
-            lat["graph_subjects_per_s"] = spb2 / (a_.elapsed_time(b__) / 50 * 1e-3)
-            lat["graph_finite"] = bool(torch.isfinite(HH).all())
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    world = max(1, args.gpus)
+    cfg = args.cfg
+    spb = args.spb or DEFAULT_SPB[cfg]
+    b = make_problem(cfg, spb, 0, 1, args.L, args.M)
+    n_sub = default_cpu_subjects(args, b, spb)
+    P_glob = spb * world
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    val, dt, kind = time_cpu(b, n_sub, steps, warm)
+    cores = os.cpu_count() or 1
+    what = ("the reference's own modules (baseline/_ref: elbo_functions.minibatch_KLD_upper_bound"
+            f"{'_iter' if isinstance(b.T, tuple) else ''} + kernel_gen.generate_kernel_batched over the GPyTorch stand-in)"
+            if kind == "reference" else "oracle port of the reference (baseline/_ref absent)")
+    frac = "all" if (n_sub == spb and world == 1) else f"{n_sub} of the {P_glob}"
+    sample = (f"{what}, torch CPU FP64 with {cores} threads: {frac} subjects of the minibatch per step (fwd + backward + NG "
+              f"update; per-subject cost is constant, the fixed M^3 part is < 3 %), {steps} steps after {warm} warm-up, "
+              f"{dt:.2f} s/step")
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": workload_config(cfg, spb, world, b),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    emit(line)
+    return 0
+
+
+def main():
+    args = parse()
+    _quiet_stdout()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = args.cfg
+    spb = args.spb or DEFAULT_SPB[cfg]
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from lvae_b200 import _lib
+    _lib.load()
+
+    exchange_note = None
+    if dist is not None and args.exchange == "p2p":       # all ranks agree on the exchange path before any timed work
+        ok = 1
+        try:
+            from lvae_b200 import distributed as D
+            D.peer_stats(dist.group.WORLD, 64, device)
         except Exception as ex:
-            lat["graph_unavailable"] = repr(ex)[:160]
+            ok, exchange_note = 0, f"symmetric memory unavailable ({repr(ex)[:120]}): NCCL all-reduce"
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            args.exchange = "nccl"
+            exchange_note = exchange_note or "a peer could not map symmetric memory: NCCL all-reduce"
 
-    if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            n_sub = min(args.cpu_subjects, args.spb)
-            v, dt = time_cpu(make_problem(cfg, args.spb, 0, 1, args.L, args.M), n_sub, 3, 1)
-            cores = os.cpu_count() or 1
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"oracle port of the reference (torch CPU FP64, {cores} threads): {n_sub} of the {args.spb} "
-                             f"subjects per step, fwd + backward + NG update, 3 steps after 1 warm-up ({dt:.2f} s/step)"}
-        gpu_ref = None
-        if world == 1 and not args.no_cpu_baseline:
+    peak = dgemm_peak_tflops(device)
+    R = run_config(args, cfg, spb, rank, world, device, dist, peak, steps=args.steps, warmup=args.warmup, headline=True,
+                   L=args.L, M=args.M)
+    o = R.out
+    b, st = R.b, R.st
+    L, M = b.L, b.M
+
+    lat = None
+    if not args.no_latency_point and rank == 0 and world == 1 and spb >= 20:
+        lat = latency_point(args, R, device)
+
+    cpu = gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sub = default_cpu_subjects(args, b, spb)
+        v, dt, kind = time_cpu(make_problem(cfg, spb, 0, 1, args.L, args.M), n_sub, 3, 1)
+        cores = os.cpu_count() or 1
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": (f"{'the reference own modules from baseline/_ref' if kind == 'reference' else 'oracle port of the reference'}"
+                          f" (torch CPU FP64, {cores} threads): {n_sub} of the {spb} subjects per step, fwd + backward + NG "
+                          f"update, 3 steps after 1 warm-up ({dt:.2f} s/step)")}
+        try:
+            v, ms = time_gpu_reference(make_problem(cfg, spb, 0, 1, args.L, args.M), device)
+            gpu_ref = {"value": v, "unit": UNIT, "ms_per_step": ms,
+                       "what": "oracle port of the reference with stock PyTorch CUDA ops (ATen/cuBLAS/cuSOLVER) on this "
+                               "GPU, device-resident inputs, all subjects of the minibatch, fwd + backward + NG update"}
+        except Exception as ex:   # the baseline is informative only
+            gpu_ref = {"unavailable": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+
+    others = {}
+    if not args.no_others and cfg == "cfg2" and args.L is None and args.M is None:
+        plan = [("cfg3", dict(cfg="cfg3", spb=DEFAULT_SPB["cfg3"])),
+                ("cfg4", dict(cfg="cfg4", spb=DEFAULT_SPB["cfg4"])),
+                ("cfg5", dict(cfg="cfg5", spb=DEFAULT_SPB["cfg5"]))]
+        if world > 1:
+            plan += [("cfg3_strong", dict(cfg="cfg3", spb=1000, strong=True)),
+                     ("cfg2_strong", dict(cfg="cfg2", spb=1000, strong=True))]
+        for name, kw in plan:
             try:
-                v, ms = time_gpu_reference(make_problem(cfg, args.spb, 0, 1, args.L, args.M), device)
-                gpu_ref = {"value": v, "unit": UNIT, "ms_per_step": ms,
-                           "what": "oracle port of the reference with stock PyTorch CUDA ops (ATen/cuBLAS/cuSOLVER) on this "
-                                   "GPU, device-resident inputs, all subjects of the minibatch, fwd + backward + NG update"}
-            except Exception as ex:   # the baseline is informative only
-                gpu_ref = {"unavailable": repr(ex)[:200]}
-        subj_ms = float(phase_ms[:, 2].mean())
-        achieved = fl["subjects"] / (subj_ms * 1e-3) * 1e-12
+                r = run_config(args, kw["cfg"], kw["spb"], rank, world, device, dist, peak, steps=args.others_steps,
+                               warmup=3, strong=kw.get("strong", False))
+                oo = r.out
+                others[name] = {"config": workload_config(kw["cfg"], kw["spb"], world, r.b, kw.get("strong", False)),
+                                "value": oo["value"], "unit": UNIT, "ms_per_step": oo["ms_per_step"],
+                                "scaling": oo["scaling"], "steps": args.others_steps, "warmup": 3,
+                                "e2e": {k: oo["e2e"][k] for k in ("value", "ms_per_step", "plain_loop_value",
+                                                                   "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                                "roofline_frac": oo["roofline_frac"], "subject_pass_tflops": oo["subject_pass_tflops"],
+                                "step_tflops": oo["step_tflops"], "phase_ms": oo["phase_ms"], "parity": oo["parity"],
+                                "kernel_path": oo["kernel_path"], "gpu_launches": oo["gpu_launches"], "finite": oo["finite"]}
+                del r
+            except Exception as ex:
+                others[name] = {"failed": repr(ex)[:300]}
+            torch.cuda.empty_cache()
+
+    rc = 0
+    if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else None
         roof_kernel = ("subject pass (fused kernel blocks + trisolve + S/Y contractions, FP64 DMMA)" if M <= 64 else
                        "subject pass (k_uv + S = U^T U GEMM + Y = V W GEMM + k_adj, FP64 DMMA)")
         traffic = None
-        tfile = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tfile) and M <= 64 and T_max <= 24:
-            ent = json.load(open(tfile)).get(f"{cfg}:spb{P_b}:k_subjects_fused2")
+        tfile = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tfile):
+            ent = json.load(open(tfile)).get(f"{cfg}:spb{spb}")
             traffic = ent["traffic_bytes"] if ent else None
+        subj_ms = o["phase_ms"]["subjects"]
         roof = {"bound": "tensor", "kernel": roof_kernel,
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "achieved": o["subject_pass_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": o["roofline_frac"],
                 "peak_source": "cuBLAS FP64 GEMM 4096^3 measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
                                f"its HBM figure is {hbm} GB/s); DMMA issue ceiling measured 37.1 TFLOP/s (profiles/)",
-                "algorithmic_flops_per_launch": fl["subjects"], "kernel_ms": subj_ms,
-                "kernel_share_of_step": subj_ms / ms_per_step, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/)",
-                "phase_ms": {n: float(phase_ms[:, i].mean()) for i, n in
-                             enumerate(["head", "prep", "subjects", "reduce", "tail", "ng_step"])},
-                "step_algorithmic_flops": fl["step"], "step_tflops": fl["step"] / (ms_per_step * 1e-3) * 1e-12}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "algorithmic_flops_per_launch": o["flops"]["subjects"], "kernel_ms": subj_ms,
+                "kernel_share_of_step": subj_ms / o["ms_per_step"], "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu, profiles/)", "phase_ms": o["phase_ms"],
+                "step_algorithmic_flops": o["flops"]["step"], "step_tflops": o["step_tflops"]}
+        line = {"metric": METRIC, "value": o["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": o["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{cfg}: Health-MNIST-shaped synthetic, {P_b} subjects/GPU x T={b.T}, L={L}, M={M}, "
-                                       f"{st.n_comp0}+{st.n_comp1} additive components, one minibatch of {P_b * world} subjects "
-                                       f"per step (bound + all gradients + NG update)",
-                           "subjects_per_gpu": P_b, "global_batch_subjects": P_b * world, "L": L, "M": M,
-                           "sharding": (f"subjects across ranks, SVGP statistics summed by {'the peer-memory kernel over NVLink (symmetric memory)' if args.exchange == 'p2p' else 'NCCL all-reduce'}"
-                                        if world > 1 else "single GPU"),
-                           "exchange_note": exchange_note,
-                           "l2": "flushed between timed steps (256 MiB write, outside the per-step event pair)",
-                           "kernel_path": kernel_path},
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms,
-                        "how": "public API (minibatch_KLD_upper_bound + backward + natural_gradient_step); every step copies "
-                               "x, mu, log_v from pinned host memory and returns kld, d_mu, d_log_v to pinned host memory; the "
-                               "copies of neighbouring steps overlap the compute on two copy streams"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
-                "clocks": clocks.summary(),
-                "finite": finite}
+                "config": workload_config(cfg, spb, world, b),
+                "impl_details": {"subjects_per_gpu": spb,
+                                 "sharding": (f"subjects across ranks, SVGP statistics summed by {'the peer-memory kernel over NVLink (symmetric memory)' if args.exchange == 'p2p' else 'NCCL all-reduce'}"
+                                              if world > 1 else "single GPU"),
+                                 "exchange_note": exchange_note,
+                                 "l2": "flushed between timed steps (256 MiB write, outside the per-step event pair)",
+                                 "kernel_path": o["kernel_path"]},
+                "e2e": o["e2e"], "gpu_launches": o["gpu_launches"], "roofline": roof, "cpu_baseline": cpu,
+                "gpu_reference": gpu_ref, "clocks": o["clocks"], "finite": o["finite"], "parity": o["parity"]}
         if lat:
             line["latency_point"] = lat
+        if others:
+            line["other_configs"] = others
         emit(line)
+        bad = [n for n, v in [(cfg, o)] + list(others.items()) if isinstance(v.get("parity"), dict) and not v["parity"]["ok"]]
+        if bad:
+            print(f"bench: PARITY FAILED on {bad}", file=sys.stderr)
+            rc = 1
     if dist is not None:
+        flag = torch.tensor([rc], dtype=torch.int32, device=device)
+        dist.broadcast(flag, 0)
+        rc = int(flag.item())
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

@@ -26,6 +26,14 @@ class GreaterThan(torch.nn.Module):
             self.__dict__["_lower_f"] = v
         return v
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_lower_f", None)        # a checkpoint may carry a different bound: drop the cached float
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_lower_f", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def inverse_transform(self, value):
         return inv_softplus(torch.as_tensor(value) - self.lower_bound)
 

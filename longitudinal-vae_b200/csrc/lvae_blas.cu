@@ -146,15 +146,11 @@ __global__ void k_pad_out(double* __restrict__ dst, const double* __restrict__ s
 }
 
 int diag_launch(double* F, int np, int kb, int batch, double* dinv, int mode, int32_t* info, int info_mod, cudaStream_t st) {
-    static bool attr = false;
+    static SmemAttrCache attr;
     const size_t smem_max = sizeof(double) * ((size_t)256 * SLD + SMAT + 16 * 64);
     const int nr = mode == 0 ? np - 64 * kb : 64;
     const size_t smem = sizeof(double) * ((size_t)nr * SLD + SMAT + 16 * 64);
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = true;
-    }
+    if (int rc_ = lvae_ensure_smem(k_diag_block, smem_max, attr)) return rc_;
     k_diag_block<<<batch, 512, smem, st>>>(F, np, kb, dinv, mode, info, info_mod);
     LVAE_COUNT_LAUNCH();
     return lvae_cuda_rc(cudaGetLastError());

@@ -291,14 +291,10 @@ extern "C" int lvae_potri_batched_f64(const double* Lc, double* Ainv, int32_t n,
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 64) return lvae_potri_big_abi(Lc, Ainv, n, batch_stride, batch, st);
     if (n <= 32 && batch >= 64) {
-        static bool attr = false;
+        static SmemAttrCache attr;
         const size_t smem = sizeof(double) * SMALL_WARPS * 2 * n * (n | 1);
-        if (!attr) {                                        // n = 32 needs 66 KB: above the 48 KB default
-            cudaError_t ea = cudaFuncSetAttribute(k_potri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)(sizeof(double) * SMALL_WARPS * 2 * 32 * 33));
-            if (ea != cudaSuccess) return lvae_cuda_rc(ea);
-            attr = true;
-        }
+        // n = 32 needs 66 KB: above the 48 KB default
+        if (int rc_ = lvae_ensure_smem(k_potri_warp, sizeof(double) * SMALL_WARPS * 2 * 32 * 33, attr)) return rc_;
         k_potri_warp<<<(batch + SMALL_WARPS - 1) / SMALL_WARPS, 32 * SMALL_WARPS, smem, st>>>(Lc, Ainv, n, batch_stride, batch);
         LVAE_COUNT_LAUNCH();
         return lvae_cuda_rc(cudaGetLastError());

@@ -146,13 +146,9 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const __grid_constant__ GemmDes
 
 template <bool TA, bool TB>
 int launch(const GemmDesc& d, int al16, cudaStream_t st) {
-    static bool attr = false;
+    static SmemAttrCache attr;
     const size_t smem = sizeof(double) * NST * STAGE;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = true;
-    }
+    if (int rc_ = lvae_ensure_smem(k_gemm<TA, TB>, smem, attr)) return rc_;
     const dim3 grid((d.n + BN - 1) / BN, (d.m + BM - 1) / BM, (unsigned)(d.batch * d.batch2 * d.ksplit));
     k_gemm<TA, TB><<<grid, 256, smem, st>>>(d, al16);
     LVAE_COUNT_LAUNCH();

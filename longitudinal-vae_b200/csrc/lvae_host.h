@@ -6,6 +6,23 @@
 #include "lvae_common.cuh"
 
 static inline int lvae_cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: the largest value set so far is cached
+// per device, so a process that drives several GPUs sets it on each of them.
+#define LVAE_MAX_DEVICES 16
+struct SmemAttrCache { size_t v[LVAE_MAX_DEVICES] = {}; };
+template <class K>
+static inline int lvae_ensure_smem(K kernel, size_t bytes, SmemAttrCache& c) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return lvae_cuda_rc(e);
+    const bool cached = dev >= 0 && dev < LVAE_MAX_DEVICES;
+    if (!cached || bytes > c.v[dev]) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return lvae_cuda_rc(e);
+        if (cached) c.v[dev] = bytes;
+    }
+    return 0;
+}
 int lvae_make_devspec(const lvae_kernel_spec_t* ks, int Q, DevSpec* out);
 int lvae_block_offsets(const int32_t* offsets, int P_b, int64_t* off2, cudaStream_t st);
 // Stream-ordered scratch for the stand-alone ABI entry points (cudaMallocAsync from the device's default pool).  On first

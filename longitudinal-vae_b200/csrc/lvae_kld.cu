@@ -9,6 +9,9 @@
 #include <stdlib.h>
 
 #include "lvae_host.h"
+#include <mutex>
+#include <vector>
+
 #include "lvae_kld.h"
 #include "lvae_linalg.cuh"
 
@@ -608,12 +611,16 @@ __global__ void __launch_bounds__(256) k_ng_step(double* __restrict__ m, double*
 // joins it: head and prep overlap.  LVAE_NO_OVERLAP=1 keeps everything on the caller's stream.
 namespace {
 constexpr int MAXDEV = 16;
+// `waiting` lists the user streams whose head was forked and not joined yet.  The side stream is in-order and `join` is
+// re-recorded after every forked head, so waiting on it covers every head forked before; the list only says WHO still has
+// to wait (two user streams or threads may interleave head / subjects / tail calls on one device).
 struct SideStream {
     cudaStream_t st = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
-    bool pending = false;
+    std::vector<cudaStream_t> waiting;
 };
 SideStream g_side[MAXDEV];
+std::mutex g_side_mu;
 int g_overlap = -1;
 
 SideStream* side_for_current_device() {
@@ -636,10 +643,14 @@ SideStream* side_for_current_device() {
 void join_head(cudaStream_t user) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return;
+    std::lock_guard<std::mutex> lock(g_side_mu);
     SideStream* s = &g_side[dev];
-    if (s->pending) {
-        cudaStreamWaitEvent(user, s->join, 0);
-        s->pending = false;
+    for (size_t i = 0; i < s->waiting.size(); ++i) {
+        if (s->waiting[i] == user) {
+            cudaStreamWaitEvent(user, s->join, 0);
+            s->waiting.erase(s->waiting.begin() + i);
+            break;
+        }
     }
 }
 }  // namespace
@@ -661,7 +672,9 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     // overlap only pays when the prep kernel leaves SMs idle (small minibatches, the reference's default of 20 subjects per
     // batch); at throughput batch sizes the head's 512-thread CTAs just take SMs away from prep
     SideStream* side = ((int64_t)p->P_b * p->L < 148 * 32) ? side_for_current_device() : nullptr;
+    std::unique_lock<std::mutex> lock(g_side_mu, std::defer_lock);
     if (side) {
+        lock.lock();                               // fork .. record(join) is one critical section per device table
         cudaEventRecord(side->fork, user);         // everything enqueued so far (previous step's tail / NG update) comes first
         cudaStreamWaitEvent(side->st, side->fork, 0);
         hs = side->st;
@@ -680,7 +693,7 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     lvae_prof_end(0, hs);
     if (side) {
         cudaEventRecord(side->join, side->st);
-        side->pending = true;
+        side->waiting.push_back(user);
     }
     return rc;
 }
@@ -699,12 +712,8 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
         if (rc) return rc;
         const int Tm = p->T_max > 0 ? p->T_max : 1;
         const size_t s1 = prep_smem(sp, Tm, p->Q);
-        static size_t prep_attr = 0;
-        if (s1 > prep_attr) {
-            cudaError_t e = cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-            if (e != cudaSuccess) return lvae_cuda_rc(e);
-            prep_attr = s1;
-        }
+        static SmemAttrCache prep_attr;
+        if (int rc_ = lvae_ensure_smem(k_prep, s1, prep_attr)) return rc_;
         lvae_prof_begin(1, st);
         if (w.prep3) {
             rc = lvae_prep3_launch(p, sp, w, st);
@@ -717,6 +726,8 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
                                                          p->lengthscale, p->outputscale, p->noise, c, p->d_log_v,
                                                          p->workspace, p->info);
             LVAE_COUNT_LAUNCH();
+            rc = lvae_cuda_rc(cudaGetLastError());
+            if (rc) return rc;
         }
         lvae_prof_end(1, st);
         join_head(st);                             // W, a (head) are needed from here on
@@ -738,12 +749,8 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             if (rc) return rc;
         } else {
             const size_t s2 = subj_smem(Tm, p->M, p->Q);
-            static size_t subj_attr = 0;
-            if (s2 > subj_attr) {
-                cudaError_t e = cudaFuncSetAttribute(k_subjects_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
-                if (e != cudaSuccess) return lvae_cuda_rc(e);
-                subj_attr = s2;
-            }
+            static SmemAttrCache subj_attr;
+            if (int rc_ = lvae_ensure_smem(k_subjects_generic, s2, subj_attr)) return rc_;
             lvae_prof_begin(2, st);
             k_subjects_generic<<<dim3(w.nchunk, p->L), 256, s2, st>>>(sp, w, p->L, p->M, p->Q, p->P_b, Tm, p->x,
                                                                       p->offsets, p->mu, p->z, p->lengthscale,

@@ -261,22 +261,12 @@ k_ng64(double* __restrict__ m, double* __restrict__ H, const double* __restrict_
     }
 }
 
-template <class K>
-int set_smem(K kernel, size_t bytes, size_t* cached) {
-    if (bytes > *cached) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        *cached = bytes;
-    }
-    return 0;
-}
-
 }  // namespace
 
 int lvae_head64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
-    static size_t attr = 0;
+    static SmemAttrCache attr;
     const size_t smem = sizeof(double) * (4 * SMAT + 16 * 64);
-    int rc = set_smem(k_head64, smem, &attr);
+    int rc = lvae_ensure_smem(k_head64, smem, attr);
     if (rc) return rc;
     k_head64<<<dim3(2, p->L), 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->z, p->m, p->H, p->lengthscale, p->outputscale,
                                                p->eps, 0.5 * p->scale, p->workspace, p->info);
@@ -285,9 +275,9 @@ int lvae_head64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const Kld
 }
 
 int lvae_tail64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
-    static size_t attr = 0;
+    static SmemAttrCache attr;
     const size_t smem = sizeof(double) * (6 * SMAT);
-    int rc = set_smem(k_tail64, smem, &attr);
+    int rc = lvae_ensure_smem(k_tail64, smem, attr);
     if (rc) return rc;
     k_tail64<<<p->L, 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->natural_gradient, p->z, p->m, p->H, p->lengthscale,
                                       p->outputscale, 0.5 * p->scale, p->const_term / p->L, p->stats, p->workspace,
@@ -299,9 +289,9 @@ int lvae_tail64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const Kld
 
 int lvae_ng64_launch(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hi, double lr, int L,
                      int M, int32_t* info, cudaStream_t st) {
-    static size_t attr = 0;
+    static SmemAttrCache attr;
     const size_t smem = sizeof(double) * (4 * SMAT + 16 * 64);
-    int rc = set_smem(k_ng64, smem, &attr);
+    int rc = lvae_ensure_smem(k_ng64, smem, attr);
     if (rc) return rc;
     k_ng64<<<L, 512, smem, st>>>(m, H, grad_m, grad_H, Hi, lr, M, info);
     LVAE_COUNT_LAUNCH();

@@ -426,12 +426,8 @@ static int launch_prep(const lvae_kld_problem_t* p, const DevSpec& sp, const Kld
     const int ld = ld_for(Tm);
     const int gpc = groups_per_cta(Tm, p->Q), pw = gpc * NW;
     const size_t smem = sizeof(double) * (size_t)gpc * group_doubles(Tm, p->Q);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_prep_warp<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc_ = lvae_ensure_smem(k_prep_warp<NW>, smem, attr)) return rc_;
     k_prep_warp<NW><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, Tm, ld, p->x, p->offsets,
                                                                     p->mu, p->log_v, p->lengthscale, p->outputscale, p->noise,
                                                                     0.5 * p->scale, p->d_log_v, p->workspace, p->info);

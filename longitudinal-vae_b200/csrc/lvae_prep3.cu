@@ -508,12 +508,8 @@ int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
     const int nslots = slots_of(sp);
     const int gpc = groups_per_cta3<NT8, LD, NW>(nslots), pw = gpc * NW;
     const size_t smem = sizeof(double) * (size_t)gpc * group_doubles3<NT8, LD, NW>(nslots);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_prep3<NT8, LD, NW, TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc_ = lvae_ensure_smem(k_prep3<NT8, LD, NW, TU>, smem, attr)) return rc_;
     if (w.nprep % pw != 0) return LVAE_E_BADARG;
     k_prep3<NT8, LD, NW, TU><<<dim3(w.nprep / pw, p->L), pw * 32, smem, st>>>(sp, w, p->L, p->Q, p->P_b, p->N_b, nslots, p->x, p->offsets,
                                                                           p->mu, p->log_v, p->lengthscale, p->outputscale,

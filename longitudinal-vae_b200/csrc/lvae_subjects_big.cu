@@ -558,12 +558,8 @@ __global__ void __launch_bounds__(256) k_reduce_big(KldLayout w, int L, int M, c
 template <int NTW>
 int launch_uv(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const size_t smem = sizeof(double) * uv_doubles(64 * NTW, p->Q);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_uv<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc_ = lvae_ensure_smem(k_uv<NTW>, smem, attr)) return rc_;
     k_uv<NTW><<<dim3(w.nchunk, p->L), 256, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, p->x, p->mu, p->z, p->lengthscale,
                                                         p->outputscale, 0.5 * p->scale, p->d_mu, p->workspace);
     LVAE_COUNT_LAUNCH();
@@ -574,12 +570,8 @@ template <int NTW>
 int launch_adj(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int MP = 64 * NTW;
     const size_t smem = sizeof(double) * ((size_t)4 * CS * MP + (size_t)NCB * CS * RG + MP + RG + 8 * 6 * 64 + RG / 2 + GT);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_adj<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc_ = lvae_ensure_smem(k_adj<NTW>, smem, attr)) return rc_;
     k_adj<NTW><<<dim3(w.nchunk, p->L), 256, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, p->x, p->z, p->lengthscale,
                                                          p->outputscale, 0.5 * p->scale, p->workspace);
     LVAE_COUNT_LAUNCH();

@@ -396,12 +396,8 @@ k_subjects_fused(const __grid_constant__ DevSpec sp, const __grid_constant__ Kld
 template <int NC0>
 int launch_nc0(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const size_t smem = sizeof(double) * fused_smem_doubles(p->Q, w.nh) + sizeof(int) * (2 * RMAX + 4);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_subjects_fused<NC0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc_ = lvae_ensure_smem(k_subjects_fused<NC0>, smem, attr)) return rc_;
     k_subjects_fused<NC0><<<dim3(w.nchunk, p->L), 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->P_b, p->x, p->offsets,
                                                                    p->mu, p->z, p->lengthscale, p->outputscale,
                                                                    0.5 * p->scale, p->d_mu, p->workspace);

@@ -576,12 +576,8 @@ int launch2(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
     int nr = 0;
     for (int cc = 0; cc < sp.n0; ++cc) nr += sp.rbf_dim[cc] >= 0;
     const size_t smem = sizeof(double) * (common_doubles(NC0, NC0 + NC1, w.nh) + 2 * set_doubles(NC0 + NC1, nr));
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_subjects_fused2<NC0, NC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return lvae_cuda_rc(e);
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc_ = lvae_ensure_smem(k_subjects_fused2<NC0, NC1>, smem, attr)) return rc_;
     k_subjects_fused2<NC0, NC1><<<dim3(w.nchunk, p->L), 512, smem, st>>>(sp, w, p->L, p->M, p->Q, p->N_b, w.TP, nr, p->x, p->mu,
                                                                         p->z, p->lengthscale, p->outputscale,
                                                                         0.5 * p->scale, p->d_mu, p->workspace);

@@ -102,6 +102,36 @@ def disable():
     _PEER.clear()
 
 
+def reduce_grads(encoder_params=(), kernel_params=(), group=None):
+    """Make the .grad of every parameter the gradient of the GLOBAL loss after backward() through the sharded bound.
+
+    The two shard modes need OPPOSITE reductions, and wrapping the model in DistributedDataParallel (which AVERAGES every
+    gradient) is wrong for both:
+      shard="subjects": the tail runs on the summed statistics on every rank, so the gradients w.r.t. the kernel
+          hyper-parameters, the noise, m and H are already COMPLETE and identical on all ranks — they must NOT be reduced.
+          d_mu / d_log_v cover the rank's own rows only, so everything upstream of them (the encoder, and the decoder through
+          the rank's share of the reconstruction loss) holds a PARTIAL gradient: SUM over ranks.
+      shard="latents": every rank sees all rows but only its latent columns: encoder gradients AND kernel / noise gradients
+          are partial: SUM both.
+    encoder_params: parameters of the networks (partial in both modes); kernel_params: kernel modules' + likelihood's
+    parameters (and m, H when natural_gradient=False).  One flattened all_reduce per group of parameters."""
+    group = group if group is not None else elbo_functions._GROUP
+    if group is None:
+        return
+    todo = list(encoder_params)
+    if elbo_functions._SHARD == "latents":
+        todo += list(kernel_params)
+    grads = [p.grad for p in todo if p is not None and p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
 def all_reduce_stats(stats, group=None):
     """Sum the SVGP sufficient statistics over ranks in place (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)

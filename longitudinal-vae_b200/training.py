@@ -15,16 +15,48 @@ from .elbo_functions import minibatch_KLD_upper_bound, minibatch_KLD_upper_bound
 from .utils import HensmanDataLoader, SubjectSampler, VaryingLengthBatchSampler, VaryingLengthSubjectSampler
 
 
+_NG_PENDING = []      # (pinned flags, event) of natural-gradient updates whose failure flag has not been read yet
+
+
+def check_natural_gradient_errors(wait=True):
+    """Raise if a natural-gradient update hit a non-positive-definite H^-1 + lr (gH + gH^T) (torch.cholesky raises at that
+    point in the reference, training.py:133).  wait=False only looks at updates whose flags have already arrived."""
+    while _NG_PENDING:
+        flags, ev = _NG_PENDING[0]
+        if not wait and not ev.query():
+            return
+        ev.synchronize()
+        _NG_PENDING.pop(0)
+        if int(flags[3]) != 0:
+            _NG_PENDING.clear()
+            raise RuntimeError(f"cholesky: the natural-gradient update of latent {int(flags[3]) - 1} is not positive-definite "
+                               "(H^-1 + lr (grad_H + grad_H^T), training.py:131-133)")
+
+
 def natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr, check=False):
     """training.py:129-135 in one launch: iH = H^-1; iH' = iH + lr (gH + gH^T); H <- iH'^-1;
-    m <- H (iH m - lr (g_m - 2 gH m)).  Returns detached (m, H)."""
+    m <- H (iH m - lr (g_m - 2 gH m)).  Returns detached (m, H).
+    A non-positive-definite iH' raises like the reference's torch.cholesky: at once with check=True (one device sync),
+    otherwise deferred — the flag travels to pinned host memory without blocking and is looked at by the next call(s) and by
+    check_natural_gradient_errors() (hensman_training calls it after the last step)."""
+    check_natural_gradient_errors(wait=False)
     hinv = None
     tag = getattr(grad_H, "_lvae_hinv", None)          # H^-1 computed by the bound for this very H (same storage, unmodified)
     if tag is not None and tag[1] == H.data_ptr() and tag[2] == H._version and H.dtype == tag[0].dtype:
         hinv = tag[0]
     m2, H2, info = ops.ng_step(m, H, grad_m, grad_H, natural_gradient_lr, Hinv=hinv)
-    if check and int(info[3].item()) != 0:
-        raise RuntimeError(f"cholesky: natural-gradient update of latent {int(info[3].item()) - 1} is not positive-definite")
+    if check:
+        if int(info[3].item()) != 0:
+            raise RuntimeError(f"cholesky: the natural-gradient update of latent {int(info[3].item()) - 1} is not "
+                               "positive-definite (H^-1 + lr (grad_H + grad_H^T), training.py:131-133)")
+    else:
+        flags = torch.empty(4, dtype=torch.int32).pin_memory()
+        flags.copy_(info, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(H.device))
+        _NG_PENDING.append((flags, ev))
+        if len(_NG_PENDING) > 4:
+            check_natural_gradient_errors(wait=False)
     return m2.detach(), H2.detach()
 
 
@@ -40,6 +72,12 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
     cuda_graph=True (fixed T, natural-gradient mode): full minibatches run the GP side of the step as one CUDA-graph replay
     (graphed.GraphedHensmanStep); the last, shorter minibatch of an epoch takes the ordinary calls."""
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    from . import elbo_functions as _EF
+    if _EF._GROUP is not None:
+        # this loop is the reference's single-process loop: it passes the LOCAL N_batch // T as P_batch, while the sharded
+        # bound needs the GLOBAL minibatch count (distributed.enable) — refuse rather than return a wrongly scaled bound
+        raise RuntimeError("lvae_b200: hensman_training is a single-process loop; call distributed.disable() first, or drive "
+                           "the sharded bound yourself (INTEGRATION.md, 'Multi-GPU': global P_batch + distributed.reduce_grads)")
     N = len(dataset)
     assert type_KL == 'GPapprox_closed'
     if varying_T:                                                                               # training.py:69-75
@@ -125,5 +163,7 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
                 best_epoch = epoch
     if gstep is not None:
         gstep.check_errors()
+    if natural_gradient and device.type == "cuda":
+        check_natural_gradient_errors()                       # the last steps' deferred failure flags
     arr = lambda k: np.asarray(curves[k], dtype=np.float64)
     return arr("penalty"), arr("net"), arr("nll"), arr("recon"), arr("kld"), m, H, best_epoch

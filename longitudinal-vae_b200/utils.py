@@ -180,7 +180,10 @@ def batch_predict_varying_T(latent_dim, covar_module0, covar_module1, likelihood
 def batch_predict(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list, P, T,
                   id_covariate, eps):
     """GP posterior-mean prediction, exactly T rows per subject in subject-major order (utils.py:210-299).  The reference
-    reshapes by position ([P, T, Q], no id check); so does this: row blocks of T consecutive rows are the subjects."""
+    reshapes by position ([P, T, Q], no id check).  Here the rows are grouped by the id column (sorted unique ids, like
+    batch_predict_varying_T): identical for the input the reference is written for (every block of T consecutive rows is
+    one subject, ids distinct between blocks); it differs only where the reference's positional reshape would mix subjects
+    — an id recurring in non-adjacent blocks or a block holding several ids — which this function treats by id."""
     if prediction_x.shape[0] != P * T:
         raise RuntimeError(f"shape '[{P}, {T}, {prediction_x.shape[1]}]' is invalid for input of size {prediction_x.numel()}")
     return _predict_any(latent_dim, covar_module0, covar_module1, likelihoods, prediction_x, test_x, mu, zt_list,

@@ -115,3 +115,51 @@ def test_latent_slices_partition_the_latent_dimensions():
         assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
         sizes = [b - a for a, b in blocks]
         assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+
+
+def _worker_reduce_grads(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200.distributed import reduce_grads
+    res = {}
+    for shard in ("subjects", "latents"):
+        EF.set_process_group(dist.group.WORLD, "nccl", shard)
+        enc = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2))]
+        ker = [torch.nn.Parameter(torch.zeros(4))]
+        enc[0].grad = torch.full((3,), float(rank + 1))
+        enc[1].grad = torch.full((2, 2), 10.0 * (rank + 1))
+        ker[0].grad = torch.full((4,), 100.0 * (rank + 1))
+        reduce_grads(enc, ker)
+        res[shard] = (enc[0].grad.clone(), enc[1].grad.clone(), ker[0].grad.clone())
+    EF.set_process_group(None)
+    if rank == 1:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_reduce_grads_applies_the_reduction_each_shard_mode_needs(tmp_path):
+    """subjects: encoder gradients are partial (summed), kernel gradients complete (untouched); latents: both summed."""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_worker_reduce_grads, args=(2, 29100 + os.getpid() % 300, out), nprocs=2, join=True)
+    res = torch.load(out)
+    e0, e1, k = res["subjects"]
+    assert torch.equal(e0, torch.full((3,), 3.0)) and torch.equal(e1, torch.full((2, 2), 30.0))
+    assert torch.equal(k, torch.full((4,), 200.0))                 # rank 1's own, complete gradient: not reduced
+    e0, e1, k = res["latents"]
+    assert torch.equal(e0, torch.full((3,), 3.0)) and torch.equal(k, torch.full((4,), 300.0))
+
+
+def test_hensman_training_refuses_to_run_sharded():
+    import lvae_b200.elbo_functions as EF
+    from lvae_b200.training import hensman_training
+    EF.set_process_group(object())
+    try:
+        with pytest.raises(RuntimeError, match="single-process"):
+            hensman_training(None, None, 1, [], None, 'GPapprox_closed', 1, 2, None, None, None, None, None, None, 1, 1, False,
+                             6, 1.0, 2, 'mse')
+    finally:
+        EF.set_process_group(None)
