@@ -53,7 +53,10 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.logdet = o; o += L * 2;
     w.big = (p->path != 1) && lvae_big_supported(p) ? 1 : 0;
     w.MP = w.big ? (p->M <= 128 ? 128 : 256) : 0;
-    w.v2 = (((p->path == 0 || p->path == 2) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
+    // path: 0 auto, 1 generic kernels, 2 fused (newest generation that covers the shape), 3 second-generation fused kernel
+    w.v3 = (!w.big && (p->path == 0 || p->path == 2) && lvae_fused3_supported(p)) ? 1 : 0;
+    w.v2 = (w.v3 || ((p->path == 0 || p->path == 2 || p->path == 3) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
+    if (w.v3) w.nchunk = lvae_chunks3(p->P_b, p->L, p->T_max);
     w.prep3 = (p->path != 1 && p->ks.spec && lvae_prep3_supported(p, w)) ? 1 : 0;
     {
         const char* e = getenv("LVAE_PREP");          // "2": force the second-generation prep kernel (A/B measurements)
@@ -707,7 +710,8 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
     w.Bi_stride = p->sum_T2;
     const double c = 0.5 * p->scale;
     if (p->P_b > 0) {
-        if (w.v2) rc = lvae_plan_groups_launch(p, w, st);
+        if (w.v3) rc = lvae_plan_groups3_launch(p, w, st);
+        else if (w.v2) rc = lvae_plan_groups_launch(p, w, st);
         else rc = lvae_block_offsets(p->offsets, p->P_b, reinterpret_cast<int64_t*>(p->workspace + w.off2), st);
         if (rc) return rc;
         const int Tm = p->T_max > 0 ? p->T_max : 1;
@@ -744,7 +748,8 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
         bool fused = w.v2 || (p->path == 2) || (p->path == 3) || (p->path == 0 && lvae_fused_supported(p));
         if (fused) {
             lvae_prof_begin(2, st);
-            rc = w.v2 ? lvae_subjects_fused2_launch(p, sp, w, st) : lvae_subjects_fused_launch(p, sp, w, st);
+            rc = w.v3 ? lvae_subjects_fused3_launch(p, sp, w, st)
+                      : (w.v2 ? lvae_subjects_fused2_launch(p, sp, w, st) : lvae_subjects_fused_launch(p, sp, w, st));
             lvae_prof_end(2, st);
             if (rc) return rc;
         } else {

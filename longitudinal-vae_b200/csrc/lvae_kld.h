@@ -22,6 +22,7 @@ struct KldLayout {
     int64_t gtab;                       // int32 [nchunk, gstride, LVAE_F2_GT] row-group plan
     int64_t gcount;                     // int32 [nchunk]
     int TP, gstride, v2;
+    int v3;                             // third-generation fused subject pass (lvae_subjects_fused3.cu); implies v2 (L^-1 rows)
     int nh, nchunk;                     // nchunk: CTAs per latent of the subject pass
     int nprep;                          // partial rows per latent of the prep pass
     int prep3;                          // 1: third-generation prep kernel (lvae_prep3.cu)
@@ -55,6 +56,12 @@ int lvae_ng64_launch(double* m, double* H, const double* grad_m, const double* g
 bool lvae_fused2_supported(const lvae_kld_problem_t* p);
 int lvae_plan_groups_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);
 int lvae_subjects_fused2_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
+
+// third-generation fused subject pass (transposed register layout, 2 CTAs of 8 warps per SM; M <= 62)
+bool lvae_fused3_supported(const lvae_kld_problem_t* p);
+int lvae_chunks3(int P_b, int L, int T_max);
+int lvae_plan_groups3_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);
+int lvae_subjects_fused3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
 
 // 64 < M <= 256 (lvae_kld_big.cu / lvae_subjects_big.cu)
 bool lvae_big_supported(const lvae_kld_problem_t* p);

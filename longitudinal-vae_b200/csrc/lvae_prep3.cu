@@ -311,6 +311,7 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         const double* __restrict__ log_v, const double* __restrict__ ls, const double* __restrict__ os,
         const double* __restrict__ noise, double c, double* __restrict__ d_log_v, double* __restrict__ ws, int32_t* info) {
     constexpr int TP8 = 8 * NT8, NL = 32 * NW, ROWS = rows3<NT8, LD>(), TRI = ROWS * (ROWS + 1) / 2, ASZ = ROWS * LD;
+    static_assert(LD >= 8 * NT8 && ROWS == 8 * NT8, "scratch matrices must cover every row / column a tile touches");
     extern __shared__ double sm[];
     __shared__ PrepTab pt;
     __shared__ unsigned short ijt[TRI];
@@ -540,7 +541,7 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
         ns += (p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE] >= 0) + p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE + 2];
     const int T = p->T_max;
     const int nw = T <= 24 ? 1 : 4;
-    const int gpc = T <= 20 ? groups_per_cta3<3, 20, 1>(ns) : (T <= 24 ? groups_per_cta3<3, 28, 1>(ns) : groups_per_cta3<5, 44, 4>(ns));
+    const int gpc = T <= 24 ? groups_per_cta3<3, 28, 1>(ns) : groups_per_cta3<5, 44, 4>(ns);
     const int pw = gpc * nw, per_sm = nw == 1 ? 2 : 1;
     int ctas = per_sm * 148 / p->L;
     if (ctas < 1) ctas = 1;
@@ -551,7 +552,10 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
 
 int lvae_prep3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     const int T = p->T_max;
-    if (T <= 20) return launch3<3, 20, 1, true>(p, sp, w, st);
+    // The scratch matrices must hold every row and column a tile can touch (ROWS = 8 * NT8, LD >= 8 * NT8).  A former
+    // <3, 20, 1> instantiation (20 x 20 scratch for T <= 20) let the 8-wide tiles run past column 19 into the next row and past
+    // row 19 into the next matrix: correct on zero-initialised scratch, i.e. for the FIRST task of a warp only — the full-size
+    // parity check of round 2 caught the later tasks (rows 0..3 of d_log_v, L^-1) being wrong.
     if (T <= 24) return launch3<3, 28, 1, true>(p, sp, w, st);
     return launch3<5, 44, 4, false>(p, sp, w, st);
 }
