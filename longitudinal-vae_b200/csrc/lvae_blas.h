@@ -43,6 +43,8 @@ int lvae_potrf_big(double* F, int np, int batch, double* dinv, int32_t* info_slo
 int lvae_trtri_big(const double* F, const double* dinv, double* X, double* T, int np, int batch, cudaStream_t st);
 // Inv = X^T X (symmetric, full).
 int lvae_gram_big(const double* X, double* Inv, int np, int batch, cudaStream_t st);
+// Inv = F^-T X (block back substitution; with X = F^-1 this is the SPD inverse with LAPACK potrs' small residual).
+int lvae_potrs_identity_big(const double* F, const double* X, double* Inv, int np, int batch, cudaStream_t st);
 
 // SPD inverse: blocked Cholesky of F in place, X = F^-1, Inv = X^T X (symmetric, full); T scratch.
 int lvae_spd_inverse_big(double* F, double* X, double* T, double* Inv, double* dinv, int np, int batch, int32_t* info,

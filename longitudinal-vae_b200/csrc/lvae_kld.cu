@@ -54,14 +54,15 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.big = (p->path != 1) && lvae_big_supported(p) ? 1 : 0;
     w.MP = w.big ? (p->M <= 128 ? 128 : 256) : 0;
     // path: 0 auto, 1 generic kernels, 2 fused (newest generation that covers the shape), 3 second-generation fused kernel
-    w.v3 = (!w.big && (p->path == 0 || p->path == 2) && lvae_fused3_supported(p)) ? 1 : 0;
-    w.v2 = (w.v3 || ((p->path == 0 || p->path == 2 || p->path == 3) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
-    if (w.v3) w.nchunk = lvae_chunks3(p->P_b, p->L, p->T_max);
     w.prep3 = (p->path != 1 && p->ks.spec && lvae_prep3_supported(p, w)) ? 1 : 0;
     {
         const char* e = getenv("LVAE_PREP");          // "2": force the second-generation prep kernel (A/B measurements)
         if (e && e[0] == '2') w.prep3 = 0;
     }
+    // the third-generation subject pass reads the B^-1 rows that only k_prep3 exports
+    w.v3 = (!w.big && w.prep3 && (p->path == 0 || p->path == 2) && lvae_fused3_supported(p)) ? 1 : 0;
+    w.v2 = (w.v3 || ((p->path == 0 || p->path == 2 || p->path == 3) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
+    if (w.v3) w.nchunk = lvae_chunks3(p->P_b, p->L, p->T_max);
     w.nprep = w.prep3 ? lvae_prep3_rows(p) : lvae_prep_rows(p->P_b, p->L, p->T_max, p->Q);
     w.nsplit = 1;
     if (w.big) {
@@ -84,6 +85,7 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.off2 = o; o += (int64_t)p->P_b + 1;
     o += o & 1;
     w.Lrows = o; o += w.v2 ? L * (int64_t)p->N_b * w.TP : 0;
+    w.Ltrows = o; o += w.v3 ? L * (int64_t)p->N_b * w.TP : 0;
     w.bmu = o; o += w.v2 ? L * (int64_t)p->N_b : 0;
     o += o & 1;
     w.gtab = o; o += w.v2 ? ((int64_t)w.nchunk * w.gstride * LVAE_F2_GT + 1) / 2 : 0;

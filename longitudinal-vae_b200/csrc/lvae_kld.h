@@ -18,6 +18,7 @@ struct KldLayout {
     int64_t stride;                     // statistics row length
     // second-generation fused pass (lvae_subjects_fused2.cu)
     int64_t Lrows;                      // [L, N_b, TP]  rows of the per-subject L^-1 (lower triangular, zero padded)
+    int64_t Ltrows;                     // [L, N_b, TP]  rows of the per-subject L^-T (upper triangular; third-generation pass only)
     int64_t bmu;                        // [L, N_b]      B_p^-1 mu_p
     int64_t gtab;                       // int32 [nchunk, gstride, LVAE_F2_GT] row-group plan
     int64_t gcount;                     // int32 [nchunk]

@@ -65,7 +65,7 @@ k_head64(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w
         if (tid == 0) ws[w.logdet + 2 * l + role] = ld;
     }
     s_tri_inverse(A, X, n8, dinv, scratch);
-    s_gram(X, Inv, n8);                                                                // 178 / 186 (explicit inverse)
+    s_potrs_identity(A, X, Inv, n8, dinv, scratch);                                    // 178 / 186 (explicit inverse)
     if (role == 1) {
         s_store(ws + w.Hi + (size_t)l * MM, Inv, M);
         return;
@@ -237,7 +237,7 @@ k_ng64(double* __restrict__ m, double* __restrict__ H, const double* __restrict_
         const int rc = s_cholesky(A, n8, dinv, &flag);                                 // training.py:130
         if (rc && tid == 0) atomicCAS(info + 3, 0, l + 1);
         s_tri_inverse(A, X, n8, dinv, scratch);
-        s_gram(X, iH, n8);                                                             // 131
+        s_potrs_identity(A, X, iH, n8, dinv, scratch);                                 // 131
     }
     for (int e = tid; e < 64 * 64; e += 512) {                                          // 132
         const int i = e >> 6, j = e & 63;
@@ -252,7 +252,7 @@ k_ng64(double* __restrict__ m, double* __restrict__ H, const double* __restrict_
     const int rc = s_cholesky(A, n8, dinv, &flag);                                     // 133
     if (rc && tid == 0) atomicCAS(info + 3, 0, l + 1);
     s_tri_inverse(A, X, n8, dinv, scratch);
-    s_gram(X, Hn, n8);                                                                 // 134
+    s_potrs_identity(A, X, Hn, n8, dinv, scratch);                                     // 134
     s_store(Hl, Hn, M);
     if (tid < M) {
         double s = 0.0;

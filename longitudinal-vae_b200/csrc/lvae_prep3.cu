@@ -398,6 +398,16 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         }
         grp_mm<true, true, NT8, LD, NW, TU>(A2, A2, A3, T, nt8, nk4, g, q, wg);                                     // B^-1 = L^-T L^-1
         gsync<NW>(bar);
+        if (w.v3) {   // third-generation subject pass: also the rows of L^-T ([row a][k'] = L^-1[k'][a], k' >= a), zero padded to TP
+            double* gt_ = ws + w.Ltrows + ((size_t)l * N_b + r0) * w.TP;
+            int i = 0, k = gl;
+            while (k >= w.TP) { k -= w.TP; ++i; }
+            for (int e = gl; e < T * w.TP; e += NL) {
+                gt_[e] = (k >= i && k < T) ? A2[k * LD + i] : 0.0;
+                k += NL;
+                while (k >= w.TP) { k -= w.TP; ++i; }
+            }
+        }
         // ---- K0_p (+ diag v) into A1 (accumulated in place over the components) ; D1 ; adjoint of K0 = c B^-1 against d k_c / d theta
         for (int cc = 0; cc < sp.n0; ++cc) {
             const double o = pt.osc[cc];

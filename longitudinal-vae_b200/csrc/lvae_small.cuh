@@ -130,8 +130,11 @@ __device__ inline int s_cholesky(double* __restrict__ A, int n8, double* __restr
 }
 
 // X = Lc^-1 for a lower-triangular n8 x n8 factor, blocked by 8: the 8 x 8 diagonal blocks by forward substitution (one
-// thread per column), then block sub-diagonal by sub-diagonal  X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj)  on the tensor
-// pipe (one warp per block, a per-warp 8 x 8 scratch tile).  scratch: 16 * 64 doubles.  Ends with __syncthreads().
+// thread per column), then block sub-diagonal by sub-diagonal  X_ij = -L_ii^-1 (sum_{k=j}^{i-1} L_ik X_kj): the block sum on
+// the tensor pipe (one warp per block, a per-warp 8 x 8 scratch tile), L_ii^-1 applied by forward SUBSTITUTION (eight lanes,
+// one column each) — Higham's Method 1B.  Multiplying by the explicit inverse X_ii instead (Method 1C, what round 1 did)
+// measured 3-4 x LAPACK's error in grad_m / grad_H on the reference's nearly singular Kzz (cond 1e8 .. 1e9).
+// scratch: 16 * 64 doubles.  Ends with __syncthreads().
 __device__ inline void s_tri_inverse(const double* __restrict__ Lc, double* __restrict__ X, int n8,
                                      const double* __restrict__ dinv, double* __restrict__ scratch) {
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -164,19 +167,68 @@ __device__ inline void s_tri_inverse(const double* __restrict__ Lc, double* __re
             tile[g * 8 + 2 * q] = t0;
             tile[g * 8 + 2 * q + 1] = t1;
             __syncwarp();
-            double x0 = 0.0, x1 = 0.0;
+            if (lane < 8) {                       // column `lane` of the block: solve L_ii x = -tile[:, lane]
+                double xr[8];
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const double a = -X[(8 * bi + g) * SLD + 8 * bi + 4 * ks + q];
-                const double b = tile[(4 * ks + q) * 8 + g];
-                dmma884(x0, x1, a, b);
+                for (int r = 0; r < 8; ++r) {
+                    double s_ = -tile[r * 8 + lane];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < r) s_ -= Lc[(8 * bi + r) * SLD + 8 * bi + k] * xr[k];
+                    xr[r] = s_ * dinv[8 * bi + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) X[(8 * bi + r) * SLD + 8 * bj + lane] = xr[r];
             }
-            X[(8 * bi + g) * SLD + 8 * bj + 2 * q] = x0;
-            X[(8 * bi + g) * SLD + 8 * bj + 2 * q + 1] = x1;
             __syncwarp();
         }
         __syncthreads();
     }
+}
+
+// Ainv = Lc^-T X for X = Lc^-1: the second triangular solve of LAPACK's potrs with the identity as right-hand side (what
+// torch.cholesky_solve(I, L) runs, elbo_functions.py:178,186).  Blocked by 8: one warp per block COLUMN bj walks the block
+// rows bottom-up, T = X_ij - sum_{k>i} L_ki^T Ainv_kj on the tensor pipe, then L_ii^T Y = T by back substitution (eight lanes,
+// one column each).  A column only depends on itself, so the warps never synchronise with each other.  Unlike the Gram
+// product X^T X (s_gram) this keeps the residual |A Ainv - I| at LAPACK's level when A is nearly singular — the bound's
+// Kxz Kzz^-1 and Kzz^-1 S Kzz^-1 cancel against exactly that residual.  Ends with __syncthreads().
+__device__ inline void s_potrs_identity(const double* __restrict__ Lc, const double* __restrict__ X, double* __restrict__ Ainv,
+                                        int n8, const double* __restrict__ dinv, double* __restrict__ scratch) {
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int nb = n8 >> 3;
+    __syncthreads();
+    double* tile = scratch + wid * 64;
+    for (int bj = wid; bj < nb; bj += (blockDim.x >> 5)) {
+        for (int bi = nb - 1; bi >= 0; --bi) {
+            double t0 = X[(8 * bi + g) * SLD + 8 * bj + 2 * q], t1 = X[(8 * bi + g) * SLD + 8 * bj + 2 * q + 1];
+            for (int bk = bi + 1; bk < nb; ++bk) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const double a = -Lc[(8 * bk + 4 * ks + q) * SLD + 8 * bi + g];           // (L_ki^T)[g][k]
+                    const double b = Ainv[(8 * bk + 4 * ks + q) * SLD + 8 * bj + g];
+                    dmma884(t0, t1, a, b);
+                }
+            }
+            tile[g * 8 + 2 * q] = t0;
+            tile[g * 8 + 2 * q + 1] = t1;
+            __syncwarp();
+            if (lane < 8) {                       // column `lane` of the block: solve L_ii^T y = tile[:, lane], bottom-up
+                double yr[8];
+#pragma unroll
+                for (int r = 7; r >= 0; --r) {
+                    double s_ = tile[r * 8 + lane];
+#pragma unroll
+                    for (int k = 7; k >= 0; --k)
+                        if (k > r) s_ -= Lc[(8 * bi + k) * SLD + 8 * bi + r] * yr[k];
+                    yr[r] = s_ * dinv[8 * bi + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) Ainv[(8 * bi + r) * SLD + 8 * bj + lane] = yr[r];
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
 }
 
 // Ainv = X^T X (A^-1 = L^-T L^-1), full symmetric output.  Ends with __syncthreads().

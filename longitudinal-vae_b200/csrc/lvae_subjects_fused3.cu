@@ -8,26 +8,35 @@
 //     of a row group lives as its transpose in DMMA accumulator layout: lane (g, q) holds X^T[8w + g][8 tt + 2q + e].
 //     A product whose contraction runs over the ROWS t of the group takes those registers directly as A fragments (the k
 //     index of m8n8k4 may be permuted freely as long as A and B agree: DMMA e uses k = 8 tt + 2q + e), so
-//         U^T = Kxz^T L^-T,   V^T = U^T L^-1,   S += U^T U  (A = own registers, diagonal tile: B = own registers too)
-//     read only the small T x T factor (16-byte loads) or the other warps' U^T rows from shared memory;
+//         U^T = Kxz^T L^-T,   V^T = U^T L^-1      (A = own registers, B = 16-byte loads of the small T x T factor)
+//         S  += U^T U           (A = own registers, B = the other warps' U^T rows; diagonal tile: own registers for both;
+//                                every unordered tile pair is computed once: 4-5 tiles per warp)
+//     S = U^T U rather than Kxz^T V on purpose: the products U[t][i] U[t][j] commute, so S is bitwise symmetric AND its rows
+//     for inducing points with identical K0 covariates are bitwise equal however the tiles are dealt to warps.  The
+//     reference's inducing points are data rows, many of them K0-duplicates; Kzz^-1 then holds +-1/(2 eps) pairs and
+//     Kzz^-1 S Kzz^-1 is exact only up to how well those rows agree (measured: 2 x the error of grad_m with Kxz^T V);
 //   * W = c (G - Kzz^-1) is held as A fragments in registers for the whole kernel (16 doubles): Y^T = W^T V^T costs one
 //     8-byte shared load per DMMA instead of two;
 //   * inducing columns M and M+1.. of the 64-column tiles are padding; two of them carry mu and r = Kxz a - mu through the
 //     same products, so that  u = B^-1 r,  ng1 = sum Kxz^T B^-1 mu,  da = sum Kxz^T B^-1 r  and  A = sum r^T B^-1 r  come out
 //     of V^T and of the S accumulators without any extra reduction (hence M <= 62);
-//   * one CTA = 8 warps, two CTAs per SM (<= 128 registers), no warp sets: W, a and the inducing covariates are per-thread.
+//   * one CTA = 8 warps, two CTAs per SM (<= 128 registers), no warp sets: W, a and the inducing covariates are per-thread;
+//   * groups that hold ONE subject filling all NT row tiles (every group of a fixed-T minibatch) run a fully unrolled,
+//     predicate-free instance of the group body.
 //
 // Per group (whole subjects, <= 8 NT rows; plan by k_plan_groups3):
-//   B0  wait for this group's cp.async data (gathered covariates, mu, block-diagonal L^-1 and its transpose, zero filled)
+//   B0  wait for this group's cp.async data (gathered covariates, mu, block-diagonal L^-1 and L^-T, zero filled)
 //   J1  Kxz^T in registers from the covariates ; un-scaled SE component values -> FC (per-thread slots) ; products with a ->
 //       row sums of this warp ; warp 7 assembles r and takes mu, r as its columns 62, 63
 //   J2  U^T (DMMA, lower-triangular tile range) -> registers + smem ;  J3  V^T (upper range) -> registers + smem ; u
 //   B2  __syncthreads ; issue the prefetch of the next group
-//   J4  S += U^T U (4-5 tiles per warp) ;  Y^T = W^T V^T
+//   J4  S += U^T U ;  Y^T = W^T V^T
 //   J5  adjoint of Kxz = 2c u a^T + 2Y against d k_c / d theta ; d_mu ; Y^T -> smem
 //   B3  __syncthreads
 //   J6  Q = Y V^T on the subject-diagonal upper tiles ; adjoint of B_p = -(c u u^T + Q) against d K1 / d theta and the noise
-// L^-1 rows come from the prep kernel (row-major per row, zero padded to TP).  Nothing of size T x M touches HBM.
+// L^-1 and L^-T rows come from k_prep3 (row-major per row, zero padded to TP).  Nothing of size T x M touches HBM.
+#include <type_traits>
+
 #include "lvae_kld.h"
 
 namespace {
@@ -37,6 +46,7 @@ constexpr int CS = 4;              // covariate slots per component: SE column, 
 constexpr int NWARP = 8;
 constexpr int NTHR = 256;
 constexpr int COL_MU = 62, COL_R = 63;
+template <int V> using ic = std::integral_constant<int, V>;
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -70,7 +80,7 @@ template <int NC0, int NC1, int NT>
 struct Smem {
     static constexpr int RG = 8 * NT;
     static constexpr int LDT = RG;          // L^-1, L^-T      row stride == 8 (mod 16): conflict-free 16-byte row reads
-    static constexpr int LDU = RG;          // U^T [64][LDU]   same pattern (SYRK B fragments); also the a-products of J1
+    static constexpr int LDU = RG;          // U^T [64][LDU]   same pattern (B fragments of S); also the a-products of J1
     static constexpr int LDC = RG + 4;      // V^T, Y^T [64][LDC]  == 12 (mod 16): conflict-free 8-byte column reads
     static constexpr int NCT = NC0 + NC1;
     static constexpr int XCSZ = NCT * CS * RG;
@@ -93,7 +103,7 @@ struct Smem {
 };
 
 template <int NC0, int NC1, int NT>
-__global__ void __launch_bounds__(NTHR, 2)
+__global__ void __launch_bounds__(NTHR, NT <= 3 ? 2 : 1)
 k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, int L, int M, int Q, int N_b, int TP,
                   const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ z,
                   const double* __restrict__ ls, const double* __restrict__ os, double c, double* __restrict__ d_mu,
@@ -150,12 +160,13 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         for (int ks = 0; ks < 16; ++ks) wf[ks] = (cv && 4 * ks + q < M) ? Wl[(size_t)(4 * ks + q) * M + j] : 0.0;
     }
     const double aj = cv ? ws[w.a + (size_t)l * M + j] : 0.0;
-    const double ca2 = 2.0 * c * aj;
+    const double caj = c * aj;
     const int nks = (M + 3) >> 2;                    // k steps of Y^T / Q that touch real columns
 
     const int* gtab = reinterpret_cast<const int*>(ws + w.gtab) + (size_t)chunk * w.gstride * GT;
     const int ngroups = reinterpret_cast<const int*>(ws + w.gcount)[chunk];
-    const double* Lrows = ws + w.Lrows + (size_t)l * N_b * TP;
+    const double* Lrows = ws + w.Lrows + (size_t)l * N_b * TP;      // rows of the per-subject L^-1 (lower triangular)
+    const double* Ltrows = ws + w.Ltrows + (size_t)l * N_b * TP;    // rows of the per-subject L^-T (upper triangular)
 
     // S tiles of this warp: (wid, (wid + d) & 7), d = 0 .. 3, and d = 4 for wid < 4 — every unordered tile pair exactly once
     double sacc[5][2];
@@ -206,31 +217,23 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
             }
         }
         if (tid < RG) cp_async8(mus + tid, mu + (size_t)(row0 + tid) * L + l, tid < R, x);
-        // L^-1, block diagonal: Linv[t][lo + k] = Lrows[row0 + t][k]; 16-byte pieces when the subject starts on an even row
+        // L^-1 and L^-T, block diagonal: Linv[t][lo + k] = Lrows[row0 + t][k] (same for L^-T); 16-byte pieces when the subject
+        // starts on an even row.  Both exports are zero outside their triangle, so whole rows of the block are copied.
 #pragma unroll
-        for (int rep = 0; rep < (RG * RG / 2 + NTHR - 1) / NTHR; ++rep) {
+        for (int rep = 0; rep < (RG * RG + NTHR - 1) / NTHR; ++rep) {
             const int e = tid + NTHR * rep;
-            if (e < RG * RG / 2) {
-                const int t = e / (RG / 2), k = 2 * (e - t * (RG / 2));
+            if (e < RG * RG) {
+                const int which = e / (RG * RG / 2), e2 = e - which * (RG * RG / 2);
+                const int t = e2 / (RG / 2), k = 2 * (e2 - t * (RG / 2));
                 const int lo = lo_[t], hi = hi_[t];
-                const double* src = Lrows + (size_t)(row0 + t) * TP + (k - lo);
-                double* dst = Linv + t * LDT + k;
+                const double* src = (which ? Ltrows : Lrows) + (size_t)(row0 + t) * TP + (k - lo);
+                double* dst = (which ? LinvT : Linv) + t * LDT + k;
                 if ((lo & 1) == 0) {
                     cp_async16(dst, src, (k >= lo) && (k < hi), x);
                 } else {
                     cp_async8(dst, src, (k >= lo) && (k < hi), x);
                     cp_async8(dst + 1, src + 1, (k + 1 >= lo) && (k + 1 < hi), x);
                 }
-            }
-        }
-        // its transpose: LinvT[a][b] = Linv[b][a]  (consecutive threads -> consecutive b: conflict-free shared-memory writes)
-#pragma unroll
-        for (int rep = 0; rep < (RG * RG + NTHR - 1) / NTHR; ++rep) {
-            const int e = tid + NTHR * rep;
-            if (e < RG * RG) {
-                const int a = e / RG, b = e - a * RG;
-                const int lo = lo_[b];
-                cp_async8(LinvT + a * LDT + b, Lrows + (size_t)(row0 + b) * TP + (a - lo), (a >= lo) && (a <= b) && (b < R), x);
             }
         }
     };
@@ -255,7 +258,6 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         __syncthreads();
         const int* mt_ = meta + slot * GT;
         const int row0 = mt_[0], R = mt_[1];
-        const int nmt = (R + 7) >> 3;
         const double* xc = XC + buf * XCSZ;
         const double2* xc2 = reinterpret_cast<const double2*>(xc);
         const int* lo_ = lo_r + slot * RG;
@@ -263,270 +265,303 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         const bool more = gi + 1 < ngroups;
         if (more) plan_rows((gi + 1) % 3);           // next group's row blocks (its plan entry arrived with this group's data)
 
-        // ---- J1: Kxz^T from the gathered covariates ; SE-bearing f_c -> FC ; products with a -------------------------
-        double kx[NT][2];
+        // FULL: one subject that reaches into the last row tile — no tile predicates, no block-diagonal trimming
+        auto body = [&](auto FULLT) {
+            constexpr bool FULL = decltype(FULLT)::value;
+            const int nmt = FULL ? NT : ((R + 7) >> 3);
+            // ---- J1: Kxz^T from the gathered covariates ; SE-bearing f_c -> FC ; products with a ---------------------
+            double kx[NT][2];
 #pragma unroll
-        for (int tt = 0; tt < NT; ++tt) kx[tt][0] = kx[tt][1] = 0.0;
-        {
-            int fslot = 0;
+            for (int tt = 0; tt < NT; ++tt) kx[tt][0] = kx[tt][1] = 0.0;
+            {
+                int fslot = 0;
+                // one component, NM = number of mask factors known at compile time (3 = any, checked at run time)
+                auto comp = [&](auto NMT, int cc) {
+                    constexpr int NM = decltype(NMT)::value;
+                    const double o = osc[cc];
+                    const bool rbf = sp.rbf_dim[cc] >= 0;
+                    const int nm = sp.n_mask[cc];
+                    double zs[NM > 0 ? NM : 1], tg[NM > 0 ? NM : 1];    // x (+/-) z == target  <=>  categorical / binary factor is 1
 #pragma unroll
-            for (int cc = 0; cc < NC0; ++cc) {
-                const double o = osc[cc];
-                const bool rbf = sp.rbf_dim[cc] >= 0;
-                const double zr = ZC[(cc * CS) * 64 + j];
-                const double h = rbf ? hil2[sp.ls_idx[cc]] : 0.0;
-                double zm[LVAE_MAX_MASKS];
-#pragma unroll
-                for (int i = 0; i < LVAE_MAX_MASKS; ++i) zm[i] = ZC[(cc * CS + 1 + i) * 64 + j];
-#pragma unroll
-                for (int tt = 0; tt < NT; ++tt) {
-                    if (tt < nmt) {
-                        const int t0 = 8 * tt + 2 * q;
-                        bool on0 = cv && (t0 < R), on1 = cv && (t0 + 1 < R);
-#pragma unroll
-                        for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
-                            if (i < sp.n_mask[cc]) {
-                                const double2 a = xc2[((cc * CS + 1 + i) * RG + t0) >> 1];
-                                if (sp.mask_type[cc][i] == LVAE_CAT) { on0 = on0 && (a.x - zm[i] == 0.0); on1 = on1 && (a.y - zm[i] == 0.0); }
-                                else { on0 = on0 && (a.x + zm[i] == 2.0); on1 = on1 && (a.y + zm[i] == 2.0); }
-                            }
-                        }
-                        double f0 = on0 ? 1.0 : 0.0, f1 = on1 ? 1.0 : 0.0;
-                        if (rbf) {
-                            const double2 a = xc2[((cc * CS) * RG + t0) >> 1];
-                            const double d0 = a.x - zr, d1 = a.y - zr;
-                            const double e0 = exp_neg(-(d0 * d0) * h, etab), e1 = exp_neg(-(d1 * d1) * h, etab);
-                            f0 = on0 ? e0 : 0.0;
-                            f1 = on1 ? e1 : 0.0;
-                            FC[(fslot * NT + tt) * NTHR + tid] = make_double2(f0, f1);
-                        }
-                        kx[tt][0] = fma(o, f0, kx[tt][0]);
-                        kx[tt][1] = fma(o, f1, kx[tt][1]);
+                    for (int i = 0; i < NM; ++i) {
+                        const bool cat = sp.mask_type[cc][i] == LVAE_CAT;
+                        const double zv = ZC[(cc * CS + 1 + i) * 64 + j];
+                        zs[i] = cat ? -zv : zv;
+                        tg[i] = cat ? 0.0 : 2.0;
                     }
-                }
-                if (rbf) ++fslot;
-            }
-        }
-        // rho = Kxz a: products into this warp's rows of the U^T buffer, column sums of the warp, then warp 7 adds the warps
-        {
-            double2* P2 = reinterpret_cast<double2*>(UTs + j * LDU);
+                    const double zr = ZC[(cc * CS) * 64 + j];
+                    const double nh_ = rbf ? -hil2[sp.ls_idx[cc]] : 0.0;
+                    double2* fc = FC + (size_t)fslot * NT * NTHR + tid;
 #pragma unroll
-            for (int tt = 0; tt < NT; ++tt) P2[4 * tt + q] = make_double2(kx[tt][0] * aj, kx[tt][1] * aj);
-            __syncwarp();
-            for (int t = lane; t < RG; t += 32) {
-                double s = 0.0;
+                    for (int tt = 0; tt < NT; ++tt) {
+                        if (FULL || tt < nmt) {
+                            const int t0 = 8 * tt + 2 * q;
+                            bool on0 = cv, on1 = cv;
+                            if (!FULL || tt == NT - 1) { on0 = on0 && (t0 < R); on1 = on1 && (t0 + 1 < R); }
 #pragma unroll
-                for (int gg = 0; gg < 8; ++gg) s += UTs[(8 * wid + gg) * LDU + t];
-                rpart[wid * RG + t] = s;
-            }
-            __syncwarp();
-        }
-        if (wid < NWARP - 1) {
-            bar_arrive(1);
-        } else {
-            bar_sync(1);                             // the other warps' column sums are in rpart
-            for (int t = lane; t < RG; t += 32) {
-                double s = -mus[t];
-#pragma unroll
-                for (int ww = 0; ww < NWARP; ++ww) s += rpart[ww * RG + t];
-                rs[t] = t < R ? s : 0.0;
-            }
-            __syncwarp();
-            if (g == 6) {                            // column 62 = mu, column 63 = r ride through the products below
-                const double2* m2 = reinterpret_cast<const double2*>(mus);
-#pragma unroll
-                for (int tt = 0; tt < NT; ++tt) { const double2 v = m2[4 * tt + q]; kx[tt][0] = v.x; kx[tt][1] = v.y; }
-            } else if (g == 7) {
-                const double2* r2 = reinterpret_cast<const double2*>(rs);
-#pragma unroll
-                for (int tt = 0; tt < NT; ++tt) { const double2 v = r2[4 * tt + q]; kx[tt][0] = v.x; kx[tt][1] = v.y; }
-            }
-        }
-
-        // ---- J2: U^T = Kxz^T L^-T   (tile (mt, nt) contributes iff mt <= nt and both touch the same subject) -----------
-        double ut[NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            ut[nt][0] = ut[nt][1] = 0.0;
-            if (nt < nmt) {
-                const int klo = lo_[8 * nt] >> 3;
-                const double2* Lr = reinterpret_cast<const double2*>(Linv + (8 * nt + g) * LDT) + q;
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt) {
-                    if (mt <= nt && mt >= klo) {
-                        const double2 b = Lr[4 * mt];
-                        dmma(ut[nt][0], ut[nt][1], kx[mt][0], b.x);
-                        dmma(ut[nt][0], ut[nt][1], kx[mt][1], b.y);
-                    }
-                }
-            }
-        }
-        {
-            double2* U2 = reinterpret_cast<double2*>(UTs + j * LDU);
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) U2[4 * nt + q] = make_double2(ut[nt][0], ut[nt][1]);
-        }
-        // ---- J3: V^T = U^T L^-1   (mt >= nt) --------------------------------------------------------------------------
-        double vt[NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            vt[nt][0] = vt[nt][1] = 0.0;
-            if (nt < nmt) {
-                const int khi = (hi_[min(8 * nt + 7, R - 1)] + 7) >> 3;
-                const double2* Lr = reinterpret_cast<const double2*>(LinvT + (8 * nt + g) * LDT) + q;
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt) {
-                    if (mt >= nt && mt < khi) {
-                        const double2 b = Lr[4 * mt];
-                        dmma(vt[nt][0], vt[nt][1], ut[mt][0], b.x);
-                        dmma(vt[nt][0], vt[nt][1], ut[mt][1], b.y);
-                    }
-                }
-            }
-        }
-        {
-            double2* V2 = reinterpret_cast<double2*>(VTs + j * LDC);
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) V2[4 * nt + q] = make_double2(vt[nt][0], vt[nt][1]);
-            if (j == COL_R) {                        // u = B^-1 r
-                double2* u2 = reinterpret_cast<double2*>(us);
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) u2[4 * nt + q] = make_double2(vt[nt][0], vt[nt][1]);
-            }
-        }
-        __syncthreads();                             // B2: U^T, V^T, u complete ; L^-1 buffers free
-        if (more) {
-            issue_data((gi + 1) % 3, buf ^ 1);
-            if (gi + 2 < ngroups) issue_meta(gi + 2, (gi + 2) % 3);
-            cp_async_commit();
-        }
-
-        // ---- J4: S += U^T U ; Y^T = W^T V^T ----------------------------------------------------------------------------
-#pragma unroll
-        for (int d = 0; d < 5; ++d) {
-            if (d < 4 || wid < 4) {
-                const int tj = (wid + d) & 7;
-                const double2* Ur = reinterpret_cast<const double2*>(UTs + (8 * tj + g) * LDU) + q;
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt) {
-                    if (mt < nmt) {
-                        double2 b;
-                        if (d == 0) b = make_double2(ut[mt][0], ut[mt][1]);
-                        else b = Ur[4 * mt];
-                        dmma(sacc[d][0], sacc[d][1], ut[mt][0], b.x);
-                        dmma(sacc[d][0], sacc[d][1], ut[mt][1], b.y);
-                    }
-                }
-            }
-        }
-        double yacc[NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) yacc[nt][0] = yacc[nt][1] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-            if (ks < nks) {
-                const double* Vr = VTs + (4 * ks + q) * LDC + g;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    if (nt < nmt) dmma(yacc[nt][0], yacc[nt][1], wf[ks], Vr[8 * nt]);
-                }
-            }
-        }
-
-        // ---- J5: adjoint of Kxz = 2 (c u a^T + Y) against the component derivatives ; Y^T -> smem ; d_mu -------------
-        {
-            double gb[NT][2];                        // c u[t] a[j] + Y[t][j]  (the factor 2 is applied once at the end)
-            const double2* u2 = reinterpret_cast<const double2*>(us);
-#pragma unroll
-            for (int tt = 0; tt < NT; ++tt) {
-                const double2 u = u2[4 * tt + q];
-                gb[tt][0] = fma(u.x, 0.5 * ca2, yacc[tt][0]);
-                gb[tt][1] = fma(u.y, 0.5 * ca2, yacc[tt][1]);
-            }
-            int fslot = 0;
-#pragma unroll
-            for (int cc = 0; cc < NC0; ++cc) {
-                const bool rbf = sp.rbf_dim[cc] >= 0;
-                const double zr = ZC[(cc * CS) * 64 + j];
-                double zm[LVAE_MAX_MASKS];
-#pragma unroll
-                for (int i = 0; i < LVAE_MAX_MASKS; ++i) zm[i] = ZC[(cc * CS + 1 + i) * 64 + j];
-#pragma unroll
-                for (int tt = 0; tt < NT; ++tt) {
-                    if (tt < nmt) {
-                        const int t0 = 8 * tt + 2 * q;
-                        if (rbf) {
-                            const double2 f = FC[(fslot * NT + tt) * NTHR + tid];
-                            const double2 a = xc2[((cc * CS) * RG + t0) >> 1];
-                            const double d0 = a.x - zr, d1 = a.y - zr;
-                            const double p0 = gb[tt][0] * f.x, p1 = gb[tt][1] * f.y;
-                            gos[cc] += p0 + p1;
-                            gls[cc] = fma(p0, d0 * d0, fma(p1, d1 * d1, gls[cc]));
-                        } else {
-                            bool on0 = cv && (t0 < R), on1 = cv && (t0 + 1 < R);
-#pragma unroll
-                            for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
-                                if (i < sp.n_mask[cc]) {
+                            for (int i = 0; i < NM; ++i) {
+                                if (NM < 3 || i < nm) {
                                     const double2 a = xc2[((cc * CS + 1 + i) * RG + t0) >> 1];
-                                    if (sp.mask_type[cc][i] == LVAE_CAT) { on0 = on0 && (a.x - zm[i] == 0.0); on1 = on1 && (a.y - zm[i] == 0.0); }
-                                    else { on0 = on0 && (a.x + zm[i] == 2.0); on1 = on1 && (a.y + zm[i] == 2.0); }
+                                    on0 = on0 && (a.x + zs[i] == tg[i]);
+                                    on1 = on1 && (a.y + zs[i] == tg[i]);
                                 }
                             }
-                            gos[cc] += (on0 ? gb[tt][0] : 0.0) + (on1 ? gb[tt][1] : 0.0);
+                            double f0 = on0 ? 1.0 : 0.0, f1 = on1 ? 1.0 : 0.0;
+                            if (rbf) {
+                                const double2 a = xc2[((cc * CS) * RG + t0) >> 1];
+                                const double d0 = a.x - zr, d1 = a.y - zr;
+                                const double e0 = exp_neg_clamped((d0 * d0) * nh_, etab), e1 = exp_neg_clamped((d1 * d1) * nh_, etab);
+                                f0 = on0 ? e0 : 0.0;
+                                f1 = on1 ? e1 : 0.0;
+                                fc[tt * NTHR] = make_double2(f0, f1);
+                            }
+                            kx[tt][0] = fma(o, f0, kx[tt][0]);
+                            kx[tt][1] = fma(o, f1, kx[tt][1]);
                         }
                     }
+                    if (rbf) ++fslot;
+                };
+#pragma unroll 1
+                for (int cc = 0; cc < NC0; ++cc) {
+                    const int nm = sp.n_mask[cc];
+                    if (nm == 0) comp(ic<0>{}, cc);
+                    else if (nm == 1) comp(ic<1>{}, cc);
+                    else comp(ic<3>{}, cc);
                 }
-                if (rbf) ++fslot;
             }
-            double2* Y2 = reinterpret_cast<double2*>(YTs + j * LDC);
+            // rho = Kxz a: products into this warp's rows of the U^T buffer, column sums of the warp, then warp 7 adds the warps
+            {
+                double2* P2 = reinterpret_cast<double2*>(UTs + j * LDU);
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) Y2[4 * nt + q] = make_double2(yacc[nt][0], yacc[nt][1]);
-        }
-        for (int t = tid; t < R; t += NTHR) d_mu[(size_t)(row0 + t) * L + l] = -2.0 * c * us[t];
-        __syncthreads();                             // B3: Y^T complete
+                for (int tt = 0; tt < NT; ++tt) P2[4 * tt + q] = make_double2(kx[tt][0] * aj, kx[tt][1] * aj);
+                __syncwarp();
+                for (int t = lane; t < RG; t += 32) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int gg = 0; gg < 8; ++gg) s += UTs[(8 * wid + gg) * LDU + t];
+                    rpart[wid * RG + t] = s;
+                }
+                __syncwarp();
+            }
+            if (wid < NWARP - 1) {
+                bar_arrive(1);
+            } else {
+                bar_sync(1);                         // the other warps' column sums are in rpart
+                for (int t = lane; t < RG; t += 32) {
+                    double s = -mus[t];
+#pragma unroll
+                    for (int ww = 0; ww < NWARP; ++ww) s += rpart[ww * RG + t];
+                    rs[t] = t < R ? s : 0.0;
+                }
+                __syncwarp();
+                if (g == 6) {                        // column 62 = mu, column 63 = r ride through the products below
+                    const double2* m2 = reinterpret_cast<const double2*>(mus);
+#pragma unroll
+                    for (int tt = 0; tt < NT; ++tt) { const double2 v = m2[4 * tt + q]; kx[tt][0] = v.x; kx[tt][1] = v.y; }
+                } else if (g == 7) {
+                    const double2* r2 = reinterpret_cast<const double2*>(rs);
+#pragma unroll
+                    for (int tt = 0; tt < NT; ++tt) { const double2 v = r2[4 * tt + q]; kx[tt][0] = v.x; kx[tt][1] = v.y; }
+                }
+            }
 
-        // ---- J6: Q = Y V^T on subject-diagonal upper tiles ; adjoint of B_p against d K1 / d theta -------------------
-        for (int tile = wid; tile < NT * (NT + 1) / 2; tile += NWARP) {
-            int jt, i;
-            tri2(tile, jt, i);                       // i <= jt
-            if (jt < nmt && 8 * jt < hi_[min(8 * i + 7, R - 1)]) {
-                double q0 = 0.0, q1 = 0.0;
-                const double* Ya = YTs + q * LDC + 8 * i + g;
-                const double* Vb = VTs + q * LDC + 8 * jt + g;
-#pragma unroll 4
-                for (int ks = 0; ks < nks; ++ks) dmma(q0, q1, Ya[4 * ks * LDC], Vb[4 * ks * LDC]);
-                const int t = 8 * i + g;
-                const double wgt = jt > i ? 2.0 : 1.0;
+            // ---- J2: U^T = Kxz^T L^-T   (tile (mt, nt) contributes iff mt <= nt and both touch the same subject) ------
+            double ut[NT][2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int t2 = 8 * jt + 2 * q + e;
-                    if (t < R && t2 < R && lo_[t] == lo_[t2]) {
-                        const double gB = -wgt * (c * us[t] * us[t2] + (e ? q1 : q0));
-                        if (t == t2) gno += gB;
+            for (int nt = 0; nt < NT; ++nt) {
+                ut[nt][0] = ut[nt][1] = 0.0;
+                if (FULL || nt < nmt) {
+                    const int klo = FULL ? 0 : (lo_[8 * nt] >> 3);
+                    const double2* Lr = reinterpret_cast<const double2*>(Linv + (8 * nt + g) * LDT) + q;
 #pragma unroll
-                        for (int k = 0; k < NC1; ++k) {
-                            const int cc = NC0 + k;
-                            bool on = true;
-#pragma unroll
-                            for (int i2 = 0; i2 < LVAE_MAX_MASKS; ++i2) {
-                                if (i2 < sp.n_mask[cc]) {
-                                    const double a = xc[(cc * CS + 1 + i2) * RG + t], b = xc[(cc * CS + 1 + i2) * RG + t2];
-                                    on = on && ((sp.mask_type[cc][i2] == LVAE_CAT) ? (a - b == 0.0) : (a + b == 2.0));
-                                }
-                            }
-                            double f = on ? 1.0 : 0.0;
-                            if (sp.rbf_dim[cc] >= 0) {
-                                const double dd = xc[(cc * CS) * RG + t] - xc[(cc * CS) * RG + t2];
-                                const double d2 = dd * dd;
-                                f = on ? exp_neg(-d2 * hil2[sp.ls_idx[cc]], etab) : 0.0;
-                                g1ls[k] += gB * f * d2;
-                            }
-                            g1os[k] += gB * f;
+                    for (int mt = 0; mt < NT; ++mt) {
+                        if (mt <= nt && (FULL || mt >= klo)) {
+                            const double2 b = Lr[4 * mt];
+                            dmma(ut[nt][0], ut[nt][1], kx[mt][0], b.x);
+                            dmma(ut[nt][0], ut[nt][1], kx[mt][1], b.y);
                         }
                     }
                 }
             }
-        }
+            {
+                double2* U2 = reinterpret_cast<double2*>(UTs + j * LDU);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) U2[4 * nt + q] = make_double2(ut[nt][0], ut[nt][1]);
+            }
+            // ---- J3: V^T = U^T L^-1   (mt >= nt) ----------------------------------------------------------------------
+            double vt[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                vt[nt][0] = vt[nt][1] = 0.0;
+                if (FULL || nt < nmt) {
+                    const int khi = FULL ? NT : ((hi_[min(8 * nt + 7, R - 1)] + 7) >> 3);
+                    const double2* Lr = reinterpret_cast<const double2*>(LinvT + (8 * nt + g) * LDT) + q;
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt) {
+                        if (mt >= nt && (FULL || mt < khi)) {
+                            const double2 b = Lr[4 * mt];
+                            dmma(vt[nt][0], vt[nt][1], ut[mt][0], b.x);
+                            dmma(vt[nt][0], vt[nt][1], ut[mt][1], b.y);
+                        }
+                    }
+                }
+            }
+            {
+                double2* V2 = reinterpret_cast<double2*>(VTs + j * LDC);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) V2[4 * nt + q] = make_double2(vt[nt][0], vt[nt][1]);
+                if (j == COL_R) {                    // u = B^-1 r
+                    double2* u2 = reinterpret_cast<double2*>(us);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) u2[4 * nt + q] = make_double2(vt[nt][0], vt[nt][1]);
+                }
+            }
+            __syncthreads();                         // B2: U^T, V^T, u complete ; L^-1 buffers free
+            if (more) {
+                issue_data((gi + 1) % 3, buf ^ 1);
+                if (gi + 2 < ngroups) issue_meta(gi + 2, (gi + 2) % 3);
+                cp_async_commit();
+            }
+
+            // ---- J4: S += U^T U ; Y^T = W^T V^T ------------------------------------------------------------------------
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                if (d < 4 || wid < 4) {
+                    const int tj = (wid + d) & 7;
+                    const double2* Ur = reinterpret_cast<const double2*>(UTs + (8 * tj + g) * LDU) + q;
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt) {
+                        if (FULL || mt < nmt) {
+                            double2 b;
+                            if (d == 0) b = make_double2(ut[mt][0], ut[mt][1]);
+                            else b = Ur[4 * mt];
+                            dmma(sacc[d][0], sacc[d][1], ut[mt][0], b.x);
+                            dmma(sacc[d][0], sacc[d][1], ut[mt][1], b.y);
+                        }
+                    }
+                }
+            }
+            double yacc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) yacc[nt][0] = yacc[nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                if (ks < nks) {
+                    const double* Vc = VTs + (4 * ks + q) * LDC + g;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        if (FULL || nt < nmt) dmma(yacc[nt][0], yacc[nt][1], wf[ks], Vc[8 * nt]);
+                    }
+                }
+            }
+
+            // ---- J5: adjoint of Kxz = 2 (c u a^T + Y) against the component derivatives ; Y^T -> smem ; d_mu ---------
+            {
+                double gb[NT][2];                    // c u[t] a[j] + Y[t][j]  (the factor 2 is applied once at the end)
+                const double2* u2 = reinterpret_cast<const double2*>(us);
+#pragma unroll
+                for (int tt = 0; tt < NT; ++tt) {
+                    const double2 u = u2[4 * tt + q];
+                    gb[tt][0] = fma(u.x, caj, yacc[tt][0]);
+                    gb[tt][1] = fma(u.y, caj, yacc[tt][1]);
+                }
+                int fslot = 0;
+#pragma unroll
+                for (int cc = 0; cc < NC0; ++cc) {
+                    const bool rbf = sp.rbf_dim[cc] >= 0;
+                    if (rbf) {
+                        const double zr = ZC[(cc * CS) * 64 + j];
+                        const double2* fc = FC + (size_t)fslot * NT * NTHR + tid;
+                        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                        for (int tt = 0; tt < NT; ++tt) {
+                            if (FULL || tt < nmt) {
+                                const double2 f = fc[tt * NTHR];
+                                const double2 a = xc2[((cc * CS) * RG + 8 * tt + 2 * q) >> 1];
+                                const double d0 = a.x - zr, d1 = a.y - zr;
+                                const double p0 = gb[tt][0] * f.x, p1 = gb[tt][1] * f.y;
+                                a1 += p0 + p1;
+                                a2 = fma(p0, d0 * d0, fma(p1, d1 * d1, a2));
+                            }
+                        }
+                        gos[cc] += a1;
+                        gls[cc] += a2;
+                        ++fslot;
+                    } else {
+                        double zm[LVAE_MAX_MASKS];
+#pragma unroll
+                        for (int i = 0; i < LVAE_MAX_MASKS; ++i) zm[i] = ZC[(cc * CS + 1 + i) * 64 + j];
+#pragma unroll
+                        for (int tt = 0; tt < NT; ++tt) {
+                            if (FULL || tt < nmt) {
+                                const int t0 = 8 * tt + 2 * q;
+                                bool on0 = cv && (t0 < R), on1 = cv && (t0 + 1 < R);
+#pragma unroll
+                                for (int i = 0; i < LVAE_MAX_MASKS; ++i) {
+                                    if (i < sp.n_mask[cc]) {
+                                        const double2 a = xc2[((cc * CS + 1 + i) * RG + t0) >> 1];
+                                        if (sp.mask_type[cc][i] == LVAE_CAT) { on0 = on0 && (a.x - zm[i] == 0.0); on1 = on1 && (a.y - zm[i] == 0.0); }
+                                        else { on0 = on0 && (a.x + zm[i] == 2.0); on1 = on1 && (a.y + zm[i] == 2.0); }
+                                    }
+                                }
+                                gos[cc] += (on0 ? gb[tt][0] : 0.0) + (on1 ? gb[tt][1] : 0.0);
+                            }
+                        }
+                    }
+                }
+                double2* Y2 = reinterpret_cast<double2*>(YTs + j * LDC);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) Y2[4 * nt + q] = make_double2(yacc[nt][0], yacc[nt][1]);
+            }
+            for (int t = tid; t < R; t += NTHR) d_mu[(size_t)(row0 + t) * L + l] = -2.0 * c * us[t];
+            __syncthreads();                         // B3: Y^T complete
+
+            // ---- J6: Q = Y V^T on subject-diagonal upper tiles ; adjoint of B_p against d K1 / d theta ---------------
+            for (int tile = wid; tile < NT * (NT + 1) / 2; tile += NWARP) {
+                int jt, i;
+                tri2(tile, jt, i);                   // i <= jt
+                if (FULL || (jt < nmt && 8 * jt < hi_[min(8 * i + 7, R - 1)])) {
+                    double q0 = 0.0, q1 = 0.0;
+                    const double* Ya = YTs + q * LDC + 8 * i + g;
+                    const double* Vb = VTs + q * LDC + 8 * jt + g;
+#pragma unroll 5
+                    for (int ks = 0; ks < nks; ++ks) dmma(q0, q1, Ya[4 * ks * LDC], Vb[4 * ks * LDC]);
+                    const int t = 8 * i + g;
+                    const double wgt = jt > i ? 2.0 : 1.0;
+                    const double ut = us[t];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int t2 = 8 * jt + 2 * q + e;
+                        if (t < R && t2 < R && (FULL || lo_[t] == lo_[t2])) {
+                            const double gB = -wgt * fma(c * ut, us[t2], e ? q1 : q0);
+                            if (t == t2) gno += gB;
+#pragma unroll
+                            for (int k = 0; k < NC1; ++k) {
+                                const int cc = NC0 + k;
+                                bool on = true;
+#pragma unroll
+                                for (int i2 = 0; i2 < LVAE_MAX_MASKS; ++i2) {
+                                    if (i2 < sp.n_mask[cc]) {
+                                        const double a = xc[(cc * CS + 1 + i2) * RG + t], b = xc[(cc * CS + 1 + i2) * RG + t2];
+                                        on = on && ((sp.mask_type[cc][i2] == LVAE_CAT) ? (a - b == 0.0) : (a + b == 2.0));
+                                    }
+                                }
+                                double f = on ? 1.0 : 0.0;
+                                if (sp.rbf_dim[cc] >= 0) {
+                                    const double dd = xc[(cc * CS) * RG + t] - xc[(cc * CS) * RG + t2];
+                                    const double d2 = dd * dd;
+                                    f = on ? exp_neg_clamped(-d2 * hil2[sp.ls_idx[cc]], etab) : 0.0;
+                                    g1ls[k] += gB * f * d2;
+                                }
+                                g1os[k] += gB * f;
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        if (mt_[2] == 1 && R > 8 * (NT - 1)) body(std::true_type{});
+        else body(std::false_type{});
     }
 
     // ---- CTA epilogue: per-thread accumulators -> the partial statistics row of this CTA ------------------------------
@@ -671,7 +706,7 @@ int dispatch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w
 int lvae_fused3_rows(const lvae_kld_problem_t* p) { return p->T_max <= 24 ? 24 : 40; }
 
 bool lvae_fused3_supported(const lvae_kld_problem_t* p) {
-    if (!(p->M <= COL_MU && p->T_max <= 24 && p->T_max >= 1 && p->ks.n_comp0 >= 1 && p->ks.n_comp0 <= 4 && p->ks.n_comp1 >= 1 &&
+    if (!(p->M <= COL_MU && p->T_max <= 40 && p->T_max >= 1 && p->ks.n_comp0 >= 1 && p->ks.n_comp0 <= 4 && p->ks.n_comp1 >= 1 &&
           p->ks.n_comp1 <= 2 && p->ks.spec))
         return false;
     int nr = 0;                                  // SE-bearing K0 components keep their values in shared memory
@@ -679,14 +714,16 @@ bool lvae_fused3_supported(const lvae_kld_problem_t* p) {
     return nr <= 3;
 }
 
-// CTAs per latent: whole waves of two 256-thread CTAs per SM; k waves cost k * (groups per CTA + set-up)
+// CTAs per latent: whole waves of 256-thread CTAs (two per SM for 24-row groups, one for 40-row groups: shared memory);
+// k waves cost k * (groups per CTA + set-up)
 int lvae_chunks3(int P_b, int L, int T_max) {
     const int rg = T_max <= 24 ? 24 : 40;
+    const int per_sm = T_max <= 24 ? 2 : 1;
     const int spg = T_max > 0 ? (rg / T_max > 0 ? rg / T_max : 1) : 1;
     int best = 1;
     long best_cost = -1;
     for (int k = 1; k <= 8; ++k) {
-        int n = 2 * 148 * k / L;
+        int n = per_sm * 148 * k / L;
         if (n < 1) continue;
         if (n > P_b) n = P_b > 0 ? P_b : 1;
         const int per = (P_b + n - 1) / n;
@@ -707,5 +744,5 @@ int lvae_plan_groups3_launch(const lvae_kld_problem_t* p, const KldLayout& w, cu
 
 int lvae_subjects_fused3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st) {
     if (!lvae_fused3_supported(p)) return LVAE_E_TOO_LARGE;
-    return dispatch3<3>(p, sp, w, st);
+    return p->T_max <= 24 ? dispatch3<3>(p, sp, w, st) : dispatch3<5>(p, sp, w, st);
 }

@@ -253,7 +253,9 @@ def test_big_path_edge_shapes_vs_generic(P, L, M, T):
     assert abs(a["kld"] - r["kld"]) <= 1e-7 * abs(r["kld"])
     for k in r:
         if k != "kld":
-            assert rel(a[k], r[k]) < TOL, k
+            # the hyper-gradients contain Kzz^-1 twice: two correct FP64 evaluation orders (here: two of this library's own
+            # kernel paths) differ by a few 1e-6 on them when cond(Kzz) ~ 1e8 (profiles/r02_parity_*.txt)
+            assert rel(a[k], r[k]) < (1e-5 if k == "d_hyper" else TOL), k
 
 
 def test_natural_gradient_step_big_m():
