@@ -168,6 +168,12 @@ int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* g
                      int32_t L, int32_t M, double* workspace, int32_t* info, void* stream);
 int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p);
 int64_t lvae_ng_workspace_doubles(int32_t L, int32_t M);
+/* Where the head leaves what the subject pass reads, as offsets (in doubles) into `workspace`: out[0] = W = c (G - Kzz^-1),
+ * out[1] = its per-latent stride (M*M, or MP*MP zero padded for 64 < M <= 256), out[2] = a = Kzz^-1 m, out[3] = its per-latent
+ * stride (M).  Used when head / tail / natural-gradient step are sharded by LATENT across GPUs while the subject pass is
+ * sharded by subject (reduce-scatter of the statistics by latent + all-gather of W, a): a rank runs the head on its
+ * latents and the gathered W, a are written at these offsets of the all-latent problem's workspace. */
+int lvae_kld_head_offsets(const lvae_kld_problem_t* p, int64_t* out4);
 
 /* One-shot all-reduce of the statistics row over NVLink peer memory (the exchange step of the subject-sharded path):
  * out[i] = sum_r peer_r[i], summed in rank order so every GPU obtains bit-identical results.  peer_ptrs: HOST array of

@@ -19,7 +19,7 @@ EXPORTS = ["lvae_kernel_dense_f64", "lvae_kernel_blocks_f64", "lvae_potrf_batche
            "lvae_kld_stats_stride", "lvae_kld_workspace_doubles", "lvae_kld_head_f64", "lvae_kld_subjects_f64",
            "lvae_kld_tail_f64", "lvae_kld_minibatch_f64", "lvae_ng_step_f64", "lvae_launch_count", "lvae_version",
            "lvae_profile_enable", "lvae_profile_last_ms", "lvae_debug_exp_neg_f64", "lvae_kld_hinv_offset", "lvae_gemm_batched_f64", "lvae_ng_workspace_doubles", "lvae_peer_sum_f64",
-           "lvae_kernel_dense_bwd_f64", "lvae_kernel_blocks_bwd_f64"]
+           "lvae_kernel_dense_bwd_f64", "lvae_kernel_blocks_bwd_f64", "lvae_kld_head_offsets"]
 
 _dp = C.c_void_p
 
@@ -81,6 +81,8 @@ def load():
     lib.lvae_ng_workspace_doubles.restype = i64
     lib.lvae_kld_hinv_offset.argtypes = [pp]
     lib.lvae_kld_hinv_offset.restype = i64
+    lib.lvae_kld_head_offsets.argtypes = [pp, C.POINTER(C.c_int64)]
+    lib.lvae_kld_head_offsets.restype = C.c_int
     lib.lvae_debug_exp_neg_f64.argtypes = [vp, vp, i32, vp]
     lib.lvae_debug_exp_neg_f64.restype = C.c_int
     lib.lvae_profile_enable.argtypes = [i32]

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "lib", "liblvae_b200.so")
 SOURCES = ["lvae_dense.cu", "lvae_gemm.cu", "lvae_blas.cu", "lvae_kld.cu", "lvae_kld64.cu", "lvae_kld_big.cu",
-           "lvae_prep.cu", "lvae_prep3.cu", "lvae_subjects_fused.cu", "lvae_subjects_fused2.cu", "lvae_subjects_fused3.cu", "lvae_subjects_big.cu",
+           "lvae_prep.cu", "lvae_prep3.cu", "lvae_subjects_fused3.cu", "lvae_subjects_big.cu",
            "lvae_kernel_grad.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

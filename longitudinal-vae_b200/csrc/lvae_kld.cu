@@ -5,7 +5,7 @@
 //   reduce   fixed-order sum of per-chunk partials into the statistics row (deterministic, no atomics)
 //   tail     per latent : D, E, KL[q(u)||p(u)], kld, grad_m, grad_H (or d_m, d_H), Kzz adjoint -> hyper-gradients
 // Formulas and line references: SURVEY.md 8(a); elbo_functions.py:144-216, 219-307.
-// The M <= 64 fast path replaces `subjects` by the DMMA kernel of lvae_subjects_fused.cu.
+// The fast paths replace prep / subjects: lvae_prep3.cu + lvae_subjects_fused3.cu (M <= 62, T <= 40), lvae_subjects_big.cu (62 < M <= 256).
 #include <stdlib.h>
 
 #include "lvae_host.h"
@@ -53,15 +53,11 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     w.logdet = o; o += L * 2;
     w.big = (p->path != 1) && lvae_big_supported(p) ? 1 : 0;
     w.MP = w.big ? (p->M <= 128 ? 128 : 256) : 0;
-    // path: 0 auto, 1 generic kernels, 2 fused (newest generation that covers the shape), 3 second-generation fused kernel
+    // path: 0 auto, 1 generic kernels (cross-check of the fast paths), 2 = 0
     w.prep3 = (p->path != 1 && p->ks.spec && lvae_prep3_supported(p, w)) ? 1 : 0;
-    {
-        const char* e = getenv("LVAE_PREP");          // "2": force the second-generation prep kernel (A/B measurements)
-        if (e && e[0] == '2') w.prep3 = 0;
-    }
-    // the third-generation subject pass reads the B^-1 rows that only k_prep3 exports
-    w.v3 = (!w.big && w.prep3 && (p->path == 0 || p->path == 2) && lvae_fused3_supported(p)) ? 1 : 0;
-    w.v2 = (w.v3 || ((p->path == 0 || p->path == 2 || p->path == 3) && lvae_fused2_supported(p)) || w.big) ? 1 : 0;
+    // the fused subject pass (M <= 62, T <= 40) reads the L^-1 / L^-T rows that only k_prep3 exports
+    w.v3 = (!w.big && w.prep3 && p->path != 1 && lvae_fused3_supported(p)) ? 1 : 0;
+    w.v2 = (w.v3 || w.big) ? 1 : 0;               // row-group plan + L^-1 rows in the workspace
     if (w.v3) w.nchunk = lvae_chunks3(p->P_b, p->L, p->T_max);
     w.nprep = w.prep3 ? lvae_prep3_rows(p) : lvae_prep_rows(p->P_b, p->L, p->T_max, p->Q);
     w.nsplit = 1;
@@ -676,7 +672,8 @@ extern "C" int lvae_kld_head_f64(const lvae_kld_problem_t* p, void* stream) {
     join_head(user);                               // a previous head nobody joined yet (defensive)
     // overlap only pays when the prep kernel leaves SMs idle (small minibatches, the reference's default of 20 subjects per
     // batch); at throughput batch sizes the head's 512-thread CTAs just take SMs away from prep
-    SideStream* side = ((int64_t)p->P_b * p->L < 148 * 32) ? side_for_current_device() : nullptr;
+    // (P_b == 0: a head-only problem of the latent-sharded tail — its caller reads W, a right after this call, keep it in order)
+    SideStream* side = (p->P_b > 0 && (int64_t)p->P_b * p->L < 148 * 32) ? side_for_current_device() : nullptr;
     std::unique_lock<std::mutex> lock(g_side_mu, std::defer_lock);
     if (side) {
         lock.lock();                               // fork .. record(join) is one critical section per device table
@@ -712,8 +709,7 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
     w.Bi_stride = p->sum_T2;
     const double c = 0.5 * p->scale;
     if (p->P_b > 0) {
-        if (w.v3) rc = lvae_plan_groups3_launch(p, w, st);
-        else if (w.v2) rc = lvae_plan_groups_launch(p, w, st);
+        if (w.v2) rc = lvae_plan_groups3_launch(p, w, st);
         else rc = lvae_block_offsets(p->offsets, p->P_b, reinterpret_cast<int64_t*>(p->workspace + w.off2), st);
         if (rc) return rc;
         const int Tm = p->T_max > 0 ? p->T_max : 1;
@@ -747,11 +743,9 @@ extern "C" int lvae_kld_subjects_f64(const lvae_kld_problem_t* p, void* stream) 
             lvae_prof_end(3, st);
             return rc;
         }
-        bool fused = w.v2 || (p->path == 2) || (p->path == 3) || (p->path == 0 && lvae_fused_supported(p));
-        if (fused) {
+        if (w.v3) {
             lvae_prof_begin(2, st);
-            rc = w.v3 ? lvae_subjects_fused3_launch(p, sp, w, st)
-                      : (w.v2 ? lvae_subjects_fused2_launch(p, sp, w, st) : lvae_subjects_fused_launch(p, sp, w, st));
+            rc = lvae_subjects_fused3_launch(p, sp, w, st);
             lvae_prof_end(2, st);
             if (rc) return rc;
         } else {
@@ -822,6 +816,15 @@ extern "C" int lvae_kld_minibatch_f64(const lvae_kld_problem_t* p, void* stream)
 }
 
 extern "C" int64_t lvae_kld_hinv_offset(const lvae_kld_problem_t* p) { return lvae_layout(p).Hi; }
+extern "C" int lvae_kld_head_offsets(const lvae_kld_problem_t* p, int64_t* out4) {
+    if (!p || !out4) return LVAE_E_BADARG;
+    const KldLayout w = lvae_layout(p);
+    out4[0] = w.big ? w.bWp : w.W;
+    out4[1] = w.big ? (int64_t)w.MP * w.MP : (int64_t)p->M * p->M;
+    out4[2] = w.a;
+    out4[3] = p->M;
+    return 0;
+}
 extern "C" int64_t lvae_ng_workspace_doubles(int32_t L, int32_t M) { return M <= 64 ? 2 : lvae_ng_big_workspace(L, M); }
 
 extern "C" int lvae_ng_step_f64(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hinv,

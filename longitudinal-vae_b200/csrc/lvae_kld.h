@@ -22,8 +22,9 @@ struct KldLayout {
     int64_t bmu;                        // [L, N_b]      B_p^-1 mu_p
     int64_t gtab;                       // int32 [nchunk, gstride, LVAE_F2_GT] row-group plan
     int64_t gcount;                     // int32 [nchunk]
-    int TP, gstride, v2;
-    int v3;                             // third-generation fused subject pass (lvae_subjects_fused3.cu); implies v2 (L^-1 rows)
+    int TP, gstride;
+    int v2;                             // row-group plan and L^-1 rows are part of the workspace (fused pass or GEMM-based path)
+    int v3;                             // fused subject pass (lvae_subjects_fused3.cu); implies v2
     int nh, nchunk;                     // nchunk: CTAs per latent of the subject pass
     int nprep;                          // partial rows per latent of the prep pass
     int prep3;                          // 1: third-generation prep kernel (lvae_prep3.cu)
@@ -43,9 +44,6 @@ int lvae_chunks(int P_b, int L, int T_max);
 int lvae_prep_rows(int P_b, int L, int T_max, int Q);
 bool lvae_prep_warp_supported(const lvae_kld_problem_t* p);
 int lvae_prep_warp_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
-// fused DMMA subject pass for M <= 64 (lvae_subjects_fused.cu); fills the same `part` partials as the generic kernel
-bool lvae_fused_supported(const lvae_kld_problem_t* p);
-int lvae_subjects_fused_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
 
 // M <= 64 shared-memory kernels (lvae_kld64.cu)
 int lvae_head64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
@@ -53,12 +51,8 @@ int lvae_tail64_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const Kld
 int lvae_ng64_launch(double* m, double* H, const double* grad_m, const double* grad_H, const double* Hi, double lr, int L,
                      int M, int32_t* info, cudaStream_t st);
 
-// second-generation fused subject pass (two 8-warp sets per CTA, SYRK, cp.async prefetch)
-bool lvae_fused2_supported(const lvae_kld_problem_t* p);
-int lvae_plan_groups_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);
-int lvae_subjects_fused2_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, cudaStream_t st);
-
-// third-generation fused subject pass (transposed register layout, 2 CTAs of 8 warps per SM; M <= 62)
+// fused subject pass (third generation: transposed register layout, 2 CTAs of 8 warps per SM; M <= 62, T <= 40) and the
+// row-group planner it shares with the GEMM-based path
 bool lvae_fused3_supported(const lvae_kld_problem_t* p);
 int lvae_chunks3(int P_b, int L, int T_max);
 int lvae_plan_groups3_launch(const lvae_kld_problem_t* p, const KldLayout& w, cudaStream_t st);

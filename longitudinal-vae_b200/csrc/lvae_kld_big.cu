@@ -297,7 +297,7 @@ GemmDesc mm(const double* A, const double* B, double* C, int MP, int L) {
 }  // namespace
 
 bool lvae_big_supported(const lvae_kld_problem_t* p) {
-    return p->M > 64 && p->M <= LVAE_MAX_M && p->T_max <= LVAE_F2_ROWS && lvae_prep_warp_supported(p) && p->ks.n_comp0 >= 1 &&
+    return p->M > 62 && p->M <= LVAE_MAX_M && p->T_max <= LVAE_F2_ROWS && lvae_prep_warp_supported(p) && p->ks.n_comp0 >= 1 &&
            p->ks.n_comp0 <= 4 && p->ks.n_comp1 >= 1 && p->ks.n_comp0 + p->ks.n_comp1 <= 8;
 }
 

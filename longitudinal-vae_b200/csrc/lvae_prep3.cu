@@ -508,7 +508,7 @@ int slots_of(const DevSpec& sp) {
 template <int NT8, int LD, int NW>
 int groups_per_cta3(int nslots) {
     const size_t bytes = sizeof(double) * group_doubles3<NT8, LD, NW>(nslots);
-    int n = (int)((NW == 1 ? 108 * 1024 : 200 * 1024) / bytes);       // NW == 1: two CTAs per SM
+    int n = (int)((NW == 1 ? 112 * 1024 : 200 * 1024) / bytes);       // NW == 1: two CTAs per SM (2 x (112 + 1) KB of 228)
     const int cap = NW == 1 ? 8 : 4;
     if (n > cap) n = cap;
     return n < 1 ? 1 : n;
@@ -532,16 +532,10 @@ int launch3(const lvae_kld_problem_t* p, const DevSpec& sp, const KldLayout& w, 
 
 }  // namespace
 
-// third-generation prep kernel: <= 8 components, T <= 24
+// prep kernel: <= 8 components, T <= 40 (one warp per task up to 24 rows, four warps per task beyond)
 bool lvae_prep3_supported(const lvae_kld_problem_t* p, const KldLayout& w) {
     (void)w;
-    {
-        const char* e = getenv("LVAE_PREP3_LONG");       // "0": leave 24 < T <= 40 to k_prep_warp<4> (A/B measurements)
-        if (!(e && e[0] == '0')) return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 40 && p->T_max >= 1;
-    }
-    // T <= 24 (one warp per task).  For 24 < T <= 40 the 4-warps-per-task instantiation of this kernel measured slower than
-    // k_prep_warp<4> of lvae_prep.cu (7.8 vs 4.7 ms at cfg4), so that range stays with the older kernel.
-    return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 24 && p->T_max >= 1;
+    return p->ks.n_comp0 + p->ks.n_comp1 <= NCM && p->T_max <= 40 && p->T_max >= 1;
 }
 
 // partial rows per latent (= warps per latent): about one wave of CTAs

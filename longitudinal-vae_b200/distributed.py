@@ -79,7 +79,7 @@ def peer_stats(group, numel, device):
     return _PEER[key]
 
 
-def enable(group=None, exchange="nccl", shard="subjects"):
+def enable(group=None, exchange="nccl", shard="subjects", tail="replicated"):
     """Route minibatch_KLD_upper_bound[_iter] through `group` (default: WORLD).
     shard="subjects" (default): every rank passes ITS rows; P_batch / P_in_current_batch remain the GLOBAL minibatch subject
         counts; the statistics row is summed over ranks.  exchange: "nccl" (one all_reduce) | "p2p" (symmetric memory +
@@ -87,14 +87,23 @@ def enable(group=None, exchange="nccl", shard="subjects"):
     shard="latents": every rank passes the SAME minibatch and computes latents latent_slice(L, rank, world) of the bound (for
         minibatches too small to split by subject): kld_total comes back all-reduced, grad_m / grad_H all-gathered;
         gradients w.r.t. mu, log_v and the hyper-parameters cover this rank's latent columns — sum them over ranks
-        (all_reduce) for the full gradient."""
+        (all_reduce) for the full gradient.
+    tail="latents" (with shard="subjects", natural_gradient=True, L divisible by the number of ranks): the subject
+        pass stays sharded by subject, but head, tail and natural-gradient update run for L / world latents per rank: the
+        statistics rows are reduce-scattered by latent, W = c (G - Kzz^-1) and a = Kzz^-1 m all-gathered before the subject
+        pass, kld per latent and the hyper-parameter gradients all-gathered after the tail.  The returned grad_m / grad_H hold
+        this rank's latents (zeros elsewhere); training.natural_gradient_step updates those latents and all-gathers the new
+        (m, H).  Worth it when the per-latent O(M^3) work is visible next to the rank's share of the subject pass (M >= 128,
+        or strong scaling of a fixed minibatch)."""
     if not dist.is_initialized():
         raise RuntimeError("lvae_b200.distributed.enable: torch.distributed is not initialised")
     if exchange not in ("nccl", "p2p"):
         raise ValueError(exchange)
     if shard not in ("subjects", "latents"):
         raise ValueError(shard)
-    elbo_functions.set_process_group(group if group is not None else dist.group.WORLD, exchange, shard)
+    if tail not in ("replicated", "latents"):
+        raise ValueError(tail)
+    elbo_functions.set_process_group(group if group is not None else dist.group.WORLD, exchange, shard, tail)
 
 
 def disable():

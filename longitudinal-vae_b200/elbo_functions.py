@@ -23,19 +23,21 @@ _PENDING = []        # KldCall objects whose info flags have not been read yet (
 
 _EXCHANGE = "nccl"   # how the statistics row is summed over ranks: "nccl" all-reduce | "p2p" (distributed.PeerStats)
 _SHARD = "subjects"  # "subjects": every rank holds its rows of the minibatch | "latents": every rank holds its latent dimensions
+_TAIL = "replicated"  # shard="subjects" only: "replicated" (every rank runs head / tail for all latents) | "latents"
 
 
-def set_process_group(group, exchange="nccl", shard="subjects"):
+def set_process_group(group, exchange="nccl", shard="subjects", tail="replicated"):
     """shard="subjects": every rank passes ITS rows; P_batch / P_in_current_batch stay GLOBAL minibatch subject counts.
+        tail="latents": head, tail and natural-gradient update are additionally sharded by latent (ops.LatentTailKldCall).
     shard="latents": every rank passes the SAME full minibatch and computes the bound for its own slice of the latent
     dimensions (no statistics exchange: the latent dimensions are independent); see distributed.enable."""
-    global _GROUP, _EXCHANGE, _SHARD
-    _GROUP, _EXCHANGE, _SHARD = group, exchange, shard
+    global _GROUP, _EXCHANGE, _SHARD, _TAIL
+    _GROUP, _EXCHANGE, _SHARD, _TAIL = group, exchange, shard, tail
 
 
 def exchange_stats(call, group, exchange):
     """The one exchange step of the sharded path, between the subject pass and the tail (call.subjects() included)."""
-    if group is None:
+    if group is None or isinstance(call, ops.LatentTailKldCall):      # the latter reduce-scatters by latent itself
         call.subjects()
     elif exchange == "p2p":
         from . import distributed
@@ -103,6 +105,8 @@ class _KldBound(torch.autograd.Function):
         else:
             call = ops.KldCall(st, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"], meta["sum_T2"], x.device,
                                natural_gradient=meta["natural_gradient"], path=_PATH)
+        if meta.get("group") is not None and meta.get("tail") == "latents" and isinstance(call, ops.KldCall):
+            call = ops.LatentTailKldCall(call, meta["group"])
         call.bind(x, offsets, mu, log_v, z, m.reshape(L, M), H, lengthscale, outputscale, noise, meta["scale"],
                   meta["const_term"], meta["eps"])
         call.head()
@@ -122,6 +126,7 @@ class _KldBound(torch.autograd.Function):
         ctx.mark_non_differentiable(call.grad_m, call.grad_H)
         # H^-1 of the head kernel rides along for natural_gradient_step (training.py:130-131 recomputes it)
         meta["Hinv"] = (call.Hinv, H.data_ptr(), H._version)
+        meta["latent_tail"] = call if isinstance(call, ops.LatentTailKldCall) else None
         return kld, call.grad_m.view(L, M, 1), call.grad_H
 
     @staticmethod
@@ -162,9 +167,11 @@ def _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, x, offsets,
     if _GROUP is not None and _SHARD == "latents":
         return _run_latent_shard(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), hyper, meta, natural_gradient)
     meta["group"] = _GROUP
+    meta["tail"] = _TAIL if (_GROUP is not None and natural_gradient) else "replicated"
     kld, gm, gH = _KldBound.apply(mu.to(f64), log_v.to(f64), m.to(f64), H.to(f64), hyper, meta)
     if natural_gradient:
         gH._lvae_hinv = meta.get("Hinv")
+        gH._lvae_latent_tail = meta.get("latent_tail")     # grad_m / grad_H hold this rank's latents only (see ops.LatentTailKldCall)
         return kld, gm, gH
     return kld, None, None
 

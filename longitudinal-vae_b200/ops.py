@@ -224,10 +224,11 @@ class KldCall:
 
 
 class SplitKldCall:
-    """Ragged minibatches with M <= 64 whose longest subject has more than 24 rows: the subjects with at most 24 rows go
-    through the fast kernels (third-generation prep + second-generation fused subject pass), the others through the
-    T <= 40 kernels; both passes write their own statistics row, the rows are added (every batch-dependent statistic is a sum
-    over subjects) and ONE tail runs.  Same interface as KldCall; d_mu / d_log_v come back in the caller's row order."""
+    """Ragged minibatches with M <= 62 whose longest subject has more than 24 rows: the subjects with at most 24 rows go
+    through the 24-row-group instance of the fused kernels (one-warp prep tasks, two CTAs per SM), the longer ones through the
+    40-row-group instance (four-warp prep tasks); both passes write their own statistics row, the rows are added (every
+    batch-dependent statistic is a sum over subjects) and ONE tail runs.  Same interface as KldCall; d_mu / d_log_v come back
+    in the caller's row order."""
 
     def __init__(self, structure, L, M, Q, counts, device, natural_gradient=True, path=0):
         counts = np.asarray(counts, dtype=np.int64)
@@ -290,10 +291,124 @@ class SplitKldCall:
             call.raise_on_info()
 
 
+class LatentTailKldCall:
+    """Subjects sharded across ranks for the subject pass, LATENT dimensions sharded for everything that is per latent
+    (SURVEY 8e): rank r runs head, tail and the natural-gradient update for its L / world latents only.
+
+        head()      own latents: Kzz^-1, H^-1, a, G, W ; all-gather of (W, a) into the all-latent problem's workspace
+        subjects()  all latents, this rank's subjects ; reduce-scatter of the statistics rows by latent
+        tail()      own latents ; all-gather of kld per latent and of the hyper-parameter gradients (small)
+        ng_step()   own latents ; all-gather of the new (m, H)
+
+    With the replicated tail every rank repeats the O(L M^3) per-latent work, which caps strong scaling once M >= 128
+    (cfg3: 2.4 of 23 ms per step do not shrink with the number of GPUs).  Same interface as KldCall; grad_m / grad_H are
+    full-size tensors of which only this rank's latents are filled (the others are zero) — ng_step() consumes them."""
+
+    def __init__(self, full, group):
+        import torch.distributed as dist
+        self.full, self.group = full, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L, M = full.L, full.M
+        if L % self.world:
+            raise RuntimeError(f"lvae_b200: the latent-sharded tail needs L ({L}) divisible by the number of ranks ({self.world})")
+        self.L, self.M, self.Q, self.device, self.structure = L, M, full.Q, full.device, full.structure
+        self.Lo = L // self.world
+        self.l0, self.l1 = self.rank * self.Lo, (self.rank + 1) * self.Lo
+        ng = bool(full.p.natural_gradient)
+        self.own = KldCall(full.structure, self.Lo, M, full.Q, 0, 0, int(full.p.T_max), 0, full.device, ng, int(full.p.path))
+        lib = full.lib
+        offs = (C.c_int64 * 4)()
+        check(lib.lvae_kld_head_offsets(C.byref(full.p), offs), "lvae_kld_head_offsets")
+        self.wstr = int(offs[1])
+        self.W_full = full.workspace[int(offs[0]):int(offs[0]) + L * self.wstr].view(L, self.wstr)
+        self.a_full = full.workspace[int(offs[2]):int(offs[2]) + L * M].view(L, M)
+        check(lib.lvae_kld_head_offsets(C.byref(self.own.p), offs), "lvae_kld_head_offsets")
+        if int(offs[1]) != self.wstr:
+            raise RuntimeError("lvae_b200: the per-latent and the all-latent problem disagree on the kernel path")
+        self.W_own = self.own.workspace[int(offs[0]):int(offs[0]) + self.Lo * self.wstr].view(self.Lo, self.wstr)
+        self.a_own = self.own.workspace[int(offs[2]):int(offs[2]) + self.Lo * M].view(self.Lo, M)
+        e = lambda *sh: torch.empty(*sh, dtype=F64, device=full.device)
+        self.pack_own, self.pack_all = e(self.Lo, self.wstr + M), e(L, self.wstr + M)
+        nh = full.d_hyper.shape[0]
+        self.small_own, self.small_all = e(self.Lo, nh + 1), e(L, nh + 1)
+        self.kld_per_latent, self.d_hyper = e(L), e(nh, L)
+        self.d_lengthscale = self.d_hyper[:self.structure.n_ls]
+        self.d_outputscale = self.d_hyper[self.structure.n_ls:self.structure.n_ls + self.structure.n_comp]
+        self.d_noise = self.d_hyper[self.structure.n_ls + self.structure.n_comp]
+        self.grad_m = torch.zeros(L, M, dtype=F64, device=full.device)
+        self.grad_H = torch.zeros(L, M, M, dtype=F64, device=full.device)
+        self.own.p.grad_m = self.grad_m[self.l0:self.l1].data_ptr()        # the own tail writes straight into the slices
+        self.own.p.grad_H = self.grad_H[self.l0:self.l1].data_ptr()
+        self.d_mu, self.d_log_v, self.stats, self.info, self.Hinv = full.d_mu, full.d_log_v, full.stats, full.info, self.own.Hinv
+        self._empty_off = torch.zeros(1, dtype=torch.int32, device=full.device)
+        self.ng_ws = e(int(lib.lvae_ng_workspace_doubles(self.Lo, M)))
+        self.ng_info = torch.zeros(4, dtype=torch.int32, device=full.device)
+
+    def bind(self, x, offsets_dev, mu, log_v, z, m, H, lengthscale, outputscale, noise, scale, const_term, eps):
+        self.full.bind(x, offsets_dev, mu, log_v, z, m, H, lengthscale, outputscale, noise, scale, const_term, eps)
+        l0, l1 = self.l0, self.l1
+        self.own.bind(x[:0], self._empty_off, mu[:0, l0:l1], log_v[:0, l0:l1], z[l0:l1], m[l0:l1], H[l0:l1],
+                      lengthscale[:, l0:l1], outputscale[:, l0:l1], noise[l0:l1], scale, const_term * self.Lo / self.L, eps)
+        return self
+
+    def set_stats(self, t):
+        self.full.set_stats(t)
+
+    def head(self):
+        import torch.distributed as dist
+        self.own.head()
+        self.pack_own[:, :self.wstr].copy_(self.W_own)
+        self.pack_own[:, self.wstr:].copy_(self.a_own)
+        dist.all_gather_into_tensor(self.pack_all, self.pack_own, group=self.group)       # W, a of every latent
+        self.W_full.copy_(self.pack_all[:, :self.wstr])
+        self.a_full.copy_(self.pack_all[:, self.wstr:])
+
+    def subjects(self):
+        import torch.distributed as dist
+        self.full.subjects()
+        dist.reduce_scatter_tensor(self.own.stats, self.full.stats, group=self.group)     # statistics rows, by latent
+
+    def tail(self):
+        import torch.distributed as dist
+        self.own.tail()
+        self.small_own[:, 0].copy_(self.own.kld_per_latent)
+        self.small_own[:, 1:].copy_(self.own.d_hyper.t())
+        dist.all_gather_into_tensor(self.small_all, self.small_own, group=self.group)
+        self.kld_per_latent.copy_(self.small_all[:, 0])
+        self.d_hyper.copy_(self.small_all[:, 1:].t())
+
+    def run(self):
+        self.head()
+        self.subjects()
+        self.tail()
+
+    def ng_step(self, m, H, lr, gather=True):
+        """training.py:129-135 on this rank's latents, in place in m [L,M(,1)] and H [L,M,M]; then the new (m, H) of every
+        latent are all-gathered (gather=False leaves the other ranks' slices stale)."""
+        import torch.distributed as dist
+        L, M, l0, l1 = self.L, self.M, self.l0, self.l1
+        mv = m.view(L, M)
+        with torch.cuda.device(self.device):
+            check(self.full.lib.lvae_ng_step_f64(ptr(mv[l0:l1]), ptr(H[l0:l1]), ptr(self.grad_m[l0:l1]), ptr(self.grad_H[l0:l1]),
+                                                 ptr(self.own.Hinv), float(lr), self.Lo, M, ptr(self.ng_ws), ptr(self.ng_info),
+                                                 stream_ptr(self.device)), "lvae_ng_step_f64")
+        if gather:
+            dist.all_gather_into_tensor(mv, mv[l0:l1].clone(), group=self.group)
+            dist.all_gather_into_tensor(H, H[l0:l1].clone(), group=self.group)
+
+    def post_info(self):
+        self.full.post_info()
+        self.own.post_info()
+
+    def raise_on_info(self):
+        self.full.raise_on_info()
+        self.own.raise_on_info()
+
+
 def make_kld_call(structure, L, M, Q, counts, device, natural_gradient=True, path=0):
     """KldCall for a minibatch whose subjects have `counts` rows (host array), or SplitKldCall when that is faster."""
     counts = np.asarray(counts, dtype=np.int64)
-    if path == 0 and M <= 64 and counts.size and counts.max() > 24:
+    if path != 1 and M <= 62 and counts.size and counts.max() > 24:
         short = counts <= 24
         if short.any() and counts[short].sum() >= 0.1 * counts.sum():
             return SplitKldCall(structure, L, M, Q, counts, device, natural_gradient, path)

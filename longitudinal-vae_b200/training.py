@@ -40,6 +40,13 @@ def natural_gradient_step(m, H, grad_m, grad_H, natural_gradient_lr, check=False
     otherwise deferred — the flag travels to pinned host memory without blocking and is looked at by the next call(s) and by
     check_natural_gradient_errors() (hensman_training calls it after the last step)."""
     check_natural_gradient_errors(wait=False)
+    lt = getattr(grad_H, "_lvae_latent_tail", None)
+    if lt is not None:          # latent-sharded tail: this rank updates its latents, the new (m, H) are all-gathered
+        m2, H2 = m.detach().to(torch.float64).contiguous().clone(), H.detach().to(torch.float64).contiguous().clone()
+        lt.ng_step(m2, H2, natural_gradient_lr)
+        if check and int(lt.ng_info[3].item()) != 0:
+            raise RuntimeError("cholesky: the natural-gradient update is not positive-definite (training.py:131-133)")
+        return m2.view_as(m), H2
     hinv = None
     tag = getattr(grad_H, "_lvae_hinv", None)          # H^-1 computed by the bound for this very H (same storage, unmodified)
     if tag is not None and tag[1] == H.data_ptr() and tag[2] == H._version and H.dtype == tag[0].dtype:

@@ -233,12 +233,14 @@ def test_big_path_matches_generic_kernels(cfg, P, L, M, ng):
 
 
 @pytest.mark.parametrize("P,L,M,T", [(40, 3, 128, (5, 24)), (1, 2, 65, 24), (23, 2, 129, (1, 7)), (60, 2, 256, (20, 24)),
-                                     (20, 2, 72, (25, 40)), (30, 3, 40, (3, 40)), (12, 2, 60, (26, 40))])
+                                     (20, 2, 72, (25, 40)), (30, 3, 40, (3, 40)), (12, 2, 60, (26, 40)),
+                                     (25, 2, 64, (4, 24)), (9, 2, 63, 20), (14, 2, 62, (5, 40)), (11, 2, 64, (25, 40))])
 def test_big_path_edge_shapes_vs_generic(P, L, M, T):
     """Auto path against the generic kernels on awkward shapes with the 6-component cfg4 kernel: the GEMM-based path on ragged
-    groups (several subjects per 24-row group, T = 1 subjects, a single subject, M = 65 / 129 just over a 64-wide block);
-    M > 64 with subjects longer than 24 rows (generic subject pass fed by the 4-warp prep kernel); M <= 64 split by subject
-    length, and with long subjects only (first-generation fused kernel)."""
+    groups (several subjects per 24-row group, T = 1 subjects, a single subject, M = 65 / 129 just over a 64-wide block, and
+    M = 63 / 64, which the fused kernel leaves to it because its tiles carry mu and r in columns 62 / 63); M > 62 with subjects
+    longer than 24 rows (generic subject pass fed by the 4-warp prep kernel); M <= 62 split by subject length, with long
+    subjects only (40-row groups), and M = 62 exactly."""
     from lvae_b200 import synth
     b = synth.make_batch("cfg4", P=P, L=L, M=1, T=T, seed=99)                 # the data rows
     bz = synth.make_batch("cfg4", P=60, L=L, M=M, T=(5, 24), seed=98)         # inducing points, m, H from a larger set

@@ -11,7 +11,8 @@ def show(name, p):
             "%.2e" % ve["reference"][k] if k in ve["reference"] else "   -    ", "%.2e" % vd[k] if k in vd else "   -    ", p["input_rounding_floor_rank0"][k],
             p["allowance_per_tensor_rank0"][k], p["all_latents_vs_torch_cuda_oracle"]["per_tensor_rank0"][k], p["verdict_rank0"][k]))
     if "cross_rank" in p:
-        print("   cross_rank", p["cross_rank"]["ok"], "%.2e" % p["cross_rank"]["max_rel"], "bit-identical ranks:", p["cross_rank"]["ranks_bit_identical"])
+        cr = p["cross_rank"]
+        print("   cross_rank", cr["ok"], "bit-identical ranks:", cr["ranks_bit_identical"], {k: "%.1e/%.1e" % (v, cr.get("tol_per_tensor_rank0", {}).get(k, 0)) for k, v in cr["per_tensor_rank0"].items()})
 if d.get("parity"):
     show(d["config"]["workload"][:4], d["parity"])
 for n, v in d.get("other_configs", {}).items():
