@@ -71,6 +71,8 @@ def parse():
     ap.add_argument("--tail", default="auto", choices=["auto", "replicated", "latents"],
                     help="N > 1: head / tail / NG step replicated on every rank, or sharded by latent (reduce-scatter of the "
                          "statistics by latent + all-gather of W, a); auto = latents when M > 64 or for strong scaling")
+    ap.add_argument("--no-split", action="store_true", help="ragged minibatches: one call with 40-row groups for all subjects "
+                                                              "instead of splitting them by length (measurement)")
     ap.add_argument("--no-latency-point", action="store_true", help="skip the spb=20 point (the reference's default batch)")
     ap.add_argument("--no-others", action="store_true", help="skip cfg3 / cfg4 / cfg5 and the strong-scaling point")
     ap.add_argument("--no-parity", action="store_true")
@@ -239,7 +241,7 @@ def oracle_step_fn(b, n_subjects, device="cpu", latents=None, eps=None):
     P_tot = P_glob = n_subjects
     N_tot = rows
     dev = lambda t: t.to(device)
-    sel = (lambda t, d: t) if latents is None else (lambda t, d: t.index_select(d, torch.as_tensor(latents)))
+    sel = (lambda t, d: t) if latents is None else (lambda t, d: t.index_select(d, torch.as_tensor(latents, device=t.device)))
     x, mu0, lv0, z = dev(b.x[:rows]), dev(sel(b.mu[:rows], 1)), dev(sel(b.log_v[:rows], 1)), dev(sel(b.z, 0))
     k0, k1, noise, params = oracle_components(b, device, latents=latents)
     ragged = isinstance(b.T, tuple)
@@ -486,7 +488,8 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
     scale = P_tot / P_glob
 
     def new_call(group_unused=None):
-        return (ops.make_kld_call(st, L, M, Q, Tl, device, natural_gradient=True, path=args.path) if ragged else
+        return (ops.make_kld_call(st, L, M, Q, Tl, device, natural_gradient=True, path=args.path,
+                                  split=not getattr(args, "no_split", False)) if ragged else
                 ops.KldCall(st, L, M, Q, P_b, N_b, T_max, sum_T2, device, natural_gradient=True, path=args.path))
     base = new_call()
     group = dist.group.WORLD if dist is not None else None
@@ -607,9 +610,9 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
             d["ready"].record(s_in)
 
     def api_step(xd, mud, lvd):
-        if ragged:
+        if ragged:      # rows per subject from the host side of the batch, as hensman_training takes them from the loader
             kld, gm, gH = EF.minibatch_KLD_upper_bound_iter(cm0, cm1, lik, L, state["m"], state["H"], xd, mud, lvd, z,
-                                                            P_tot, P_glob, N_tot, True, 2, EPS)
+                                                            P_tot, P_glob, N_tot, True, 2, EPS, subject_counts=Tl)
         else:
             kld, gm, gH = EF.minibatch_KLD_upper_bound(cm0, cm1, lik, L, state["m"], state["H"], xd, mud, lvd, z, P_tot,
                                                        P_glob, int(b.T), True, EPS)
@@ -775,9 +778,12 @@ def check_parity(args, b, call, shcall, device_step, m, H, device, dist, rank, w
     dpick = dict(kld=None, grad_m=ref_dev["grad_m"][li], grad_H=ref_dev["grad_H"][li], d_mu=ref_dev["d_mu"][:, li],
                  d_log_v=ref_dev["d_log_v"][:, li], d_hyper=ref_dev["d_hyper"][:, li],
                  m_new=ref_dev["m_new"].reshape(L, M)[li], H_new=ref_dev["H_new"][li])
-    dev_vs_host = {k: rel_err(dpick[k], cref[k]) for k in KEYS if dpick[k] is not None}
     del ref, ref_dev
     torch.cuda.empty_cache()
+    with torch.device(device):                     # kld of exactly these latents from the torch-CUDA path (it returns a sum)
+        dpick["kld"] = oracle_step_fn(b, b.P, device=device, latents=lat)(update=False)["kld"]
+    torch.cuda.empty_cache()
+    dev_vs_host = {k: rel_err(dpick[k], cref[k]) for k in KEYS}
     tr = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in truth.items()}
     tr["kld"] = tr["kld"].sum()
     XK = ("kld", "grad_m", "grad_H", "d_mu", "d_log_v")
@@ -878,14 +884,15 @@ def check_parity(args, b, call, shcall, device_step, m, H, device, dist, rank, w
         one["d_mu"], one["d_log_v"] = full["d_mu"][r0:r0 + allrows[rank]], full["d_log_v"][r0:r0 + allrows[rank]]
         cerr = {k: rel_err(sh[k], one[k]) for k in one}
         # Yardstick: sharding only changes the ORDER in which the statistics of the subjects are summed.  So does evaluating
-        # the same gathered minibatch on one GPU with its subjects in reversed order — the spread between those two one-GPU
+        # the same gathered minibatch on one GPU with its subjects randomly permuted — the spread between those two one-GPU
         # results is what a re-ordered sum costs on this problem (Kzz^-1 amplifies the last bits of S and ng1).
         ends = np.concatenate([[0], np.cumsum(Tg)])
-        order = np.concatenate([np.arange(ends[i], ends[i + 1]) for i in range(len(Tg) - 1, -1, -1)])
+        perm = np.random.default_rng(12345).permutation(len(Tg))       # same on every rank
+        order = np.concatenate([np.arange(ends[i], ends[i + 1]) for i in perm])
         oi = torch.from_numpy(order).to(device)
-        offr = torch.from_numpy(np.concatenate([[0], np.cumsum(Tg[::-1])]).astype(np.int32)).to(device)
+        offr = torch.from_numpy(np.concatenate([[0], np.cumsum(Tg[perm])]).astype(np.int32)).to(device)
         if t["ragged"] and isinstance(big, ops.SplitKldCall):
-            big = ops.make_kld_call(t["st"], L, M, Q, Tg[::-1].copy(), device, natural_gradient=True, path=args.path)
+            big = ops.make_kld_call(t["st"], L, M, Q, Tg[perm].copy(), device, natural_gradient=True, path=args.path)
         rev = one_gpu(gx[oi], offr, gmu[oi], glv[oi])
         AMP = ("kld", "grad_m", "grad_H", "d_hyper", "m_new", "H_new")
         spread = {k: rel_err(rev[k], full[k]) for k in AMP}
@@ -903,7 +910,7 @@ def check_parity(args, b, call, shcall, device_step, m, H, device, dist, rank, w
                              "against": f"one-GPU CUDA evaluation of the gathered {int(len(Tg))}-subject minibatch on every rank; "
                                         "d_mu / d_log_v must agree to 1e-6 (they are bit-identical in practice), the outputs that "
                                         "carry Kzz^-1 to max(1e-6, 4 x the spread between two one-GPU evaluations of that minibatch "
-                                        "with its subjects in forward and in reversed order)"}
+                                        "with its subjects in the given and in a randomly permuted order)"}
         out["ok"] = bool(out["ok"] and out["cross_rank"]["ok"])
         del big
         torch.cuda.empty_cache()

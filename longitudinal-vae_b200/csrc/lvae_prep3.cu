@@ -437,14 +437,14 @@ k_prep3(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w,
         gsync<NW>(bar);
         grp_mm<false, false, NT8, LD, NW, TU>(A3, A2, A1, T, nt8, nk4, g, q, wg);                                   // X2 = B^-1 X1
         gsync<NW>(bar);
-        if (w.v2) {
+        if (w.v2 && !w.v3) {          // B^-1 mu for the GEMM-based subject pass (the fused pass carries mu through its own products)
             double* gb = ws + w.bmu + (size_t)l * N_b + r0;
             for (int t = gl; t < T; t += NL) {
                 double s = 0.0;
                 for (int k = 0; k < T; ++k) s += A3[t * LD + k] * mw[k];
                 gb[t] = s;
             }
-        } else {      // first-generation fused / generic subject pass: the explicit inverse blocks
+        } else if (!w.v2) {      // generic subject pass: the explicit inverse blocks
             double* gBi = ws + w.Bi + (size_t)l * w.Bi_stride + reinterpret_cast<const int64_t*>(ws + w.off2)[p];
             int i = 0, j = gl;
             while (j >= T) { j -= T; ++i; }
@@ -508,7 +508,9 @@ int slots_of(const DevSpec& sp) {
 template <int NT8, int LD, int NW>
 int groups_per_cta3(int nslots) {
     const size_t bytes = sizeof(double) * group_doubles3<NT8, LD, NW>(nslots);
-    int n = (int)((NW == 1 ? 112 * 1024 : 200 * 1024) / bytes);       // NW == 1: two CTAs per SM (2 x (112 + 1) KB of 228)
+    // NW == 1: two CTAs per SM.  (Measured: a sixth task per CTA, 2 x 113 KB, no longer fits two CTAs next to the kernel's
+    // static shared memory — prep went from 0.60 to 0.87 ms at cfg2.)
+    int n = (int)((NW == 1 ? 108 * 1024 : 200 * 1024) / bytes);
     const int cap = NW == 1 ? 8 : 4;
     if (n > cap) n = cap;
     return n < 1 ? 1 : n;

@@ -307,16 +307,42 @@ def group_by_subject(ids):
             int((counts_h * counts_h).sum()))
 
 
+def subject_counts_of(id_column):
+    """Rows per subject when the rows of every subject are CONTIGUOUS (what the reference's samplers produce, utils.py:79-113),
+    else None.  `id_column`: host tensor / array of the id covariate of a minibatch — call it on the loader's CPU batch, before
+    the copy to the device, and pass the result as `subject_counts=`: the bound then needs no torch.unique and no
+    device->host synchronisation to find its subjects."""
+    ids = torch.as_tensor(id_column).reshape(-1).cpu()
+    if ids.numel() == 0:
+        return np.zeros(0, dtype=np.int64)
+    uniq, counts = torch.unique_consecutive(ids, return_counts=True)
+    if torch.unique(uniq).numel() != uniq.numel():          # an id comes back after another subject: rows are not grouped
+        return None
+    return counts.numpy().astype(np.int64)
+
+
 def minibatch_KLD_upper_bound_iter(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, mu, log_v, z, P,
-                                   P_in_current_batch, N, natural_gradient, id_covariate, eps):
+                                   P_in_current_batch, N, natural_gradient, id_covariate, eps, subject_counts=None):
     """Same bound for irregular numbers of rows per subject (elbo_functions.py:219-307): subjects are the sorted unique
-    values of column `id_covariate`; the constant term is L*N/2 with N the number of rows of the whole data set."""
-    order, offsets, T_max, sum_T2 = group_by_subject(train_xt[:, id_covariate])
-    if order is not None:
-        train_xt, mu, log_v = train_xt[order], mu[order], log_v[order]
+    values of column `id_covariate`; the constant term is L*N/2 with N the number of rows of the whole data set.
+    subject_counts (optional, not in the reference): host array of rows per subject for a minibatch whose subjects occupy
+    contiguous row blocks (see subject_counts_of) — the grouping of lines 264-267 is then known without looking at the ids on
+    the device; the bound is a sum over subjects, so their order does not matter."""
+    if subject_counts is not None:
+        counts = np.asarray(subject_counts, dtype=np.int64)
+        if int(counts.sum()) != train_xt.shape[0]:
+            raise RuntimeError("lvae_b200: subject_counts does not add up to the number of rows of the minibatch")
+        off = np.zeros(counts.size + 1, dtype=np.int32)
+        np.cumsum(counts, out=off[1:])
+        offsets = torch.from_numpy(off).to(train_xt.device, non_blocking=True)
+        T_max, sum_T2 = int(counts.max()) if counts.size else 0, int((counts * counts).sum())
+    else:
+        order, offsets, T_max, sum_T2 = group_by_subject(train_xt[:, id_covariate])
+        if order is not None:
+            train_xt, mu, log_v = train_xt[order], mu[order], log_v[order]
+        counts = group_by_subject.last_counts
     kld, gm, gH = _run(covar_module0, covar_module1, likelihood, latent_dim, m, H, train_xt, offsets, T_max, sum_T2, mu,
-                       log_v, z, P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps,
-                       counts=group_by_subject.last_counts)
+                       log_v, z, P / P_in_current_batch, latent_dim * N / 2, natural_gradient, eps, counts=counts)
     return kld.reshape(1), gm, gH
 
 

@@ -405,10 +405,11 @@ class LatentTailKldCall:
         self.own.raise_on_info()
 
 
-def make_kld_call(structure, L, M, Q, counts, device, natural_gradient=True, path=0):
-    """KldCall for a minibatch whose subjects have `counts` rows (host array), or SplitKldCall when that is faster."""
+def make_kld_call(structure, L, M, Q, counts, device, natural_gradient=True, path=0, split=True):
+    """KldCall for a minibatch whose subjects have `counts` rows (host array), or SplitKldCall when that is faster
+    (split=False: always one call)."""
     counts = np.asarray(counts, dtype=np.int64)
-    if path != 1 and M <= 62 and counts.size and counts.max() > 24:
+    if split and path != 1 and M <= 62 and counts.size and counts.max() > 24:
         short = counts <= 24
         if short.any() and counts[short].sum() >= 0.1 * counts.sum():
             return SplitKldCall(structure, L, M, Q, counts, device, natural_gradient, path)

@@ -11,7 +11,7 @@ import torch
 from torch.utils.data.sampler import BatchSampler
 
 from . import ops
-from .elbo_functions import minibatch_KLD_upper_bound, minibatch_KLD_upper_bound_iter
+from .elbo_functions import minibatch_KLD_upper_bound, minibatch_KLD_upper_bound_iter, subject_counts_of
 from .utils import HensmanDataLoader, SubjectSampler, VaryingLengthBatchSampler, VaryingLengthSubjectSampler
 
 
@@ -129,10 +129,14 @@ def hensman_training(nnet_model, type_nnet, epochs, dataset, optimiser, type_KL,
                 P_in_current_batch = subjects_per_batch
                 kld_loss = gstep(train_x, mu, log_var)
             elif varying_T:                                                                      # 110-115
-                P_in_current_batch = torch.unique(train_x[:, id_covariate]).shape[0]
+                # the samplers deliver every subject as one contiguous block: count its rows on the loader's CPU batch
+                # (no torch.unique on the device, no synchronisation); otherwise fall back to the reference's grouping
+                counts = subject_counts_of(sample_batched['label'][:, id_covariate])
+                P_in_current_batch = (len(counts) if counts is not None else
+                                      torch.unique(train_x[:, id_covariate]).shape[0])
                 kld_loss, grad_m, grad_H = minibatch_KLD_upper_bound_iter(
                     covar_module0, covar_module1, likelihoods, latent_dim, m, PSD_H, train_x, mu, log_var, zt_list, P,
-                    P_in_current_batch, N, natural_gradient, id_covariate, eps)
+                    P_in_current_batch, N, natural_gradient, id_covariate, eps, subject_counts=counts)
             else:
                 P_in_current_batch = N_batch // T
                 kld_loss, grad_m, grad_H = minibatch_KLD_upper_bound(
