@@ -187,6 +187,37 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const double* __restrict_
 // C ABI (include/lvae_b200.h): one batch dimension.  A product with few output tiles and a long k (S = Kxz^T B^-1 Kxz over
 // all rows of a data set: 60 x 60 x 20 000) would leave most of the 148 SMs idle, so the k range is split over ~2 waves of
 // CTAs into a scratch buffer and summed in a fixed order.
+// Stacks of thousands of tiny products (the per-subject T x T blocks of the non-minibatch bounds and of the predictors,
+// elbo_functions.py:61-63,113-115, utils.py:165-190: B_p^-1 K0xz_p, B_p^-1 mu_p and their adjoints): one 128-thread CTA per
+// matrix, 8 x 8 output tiles dealt to its four warps, DMMA fragments read straight from global memory (the operands of one
+// product are a few KB and stay in L1).  A 128 x 64 tile of the large-matrix kernel above would be > 90 % padding here.
+__global__ void __launch_bounds__(128) k_gemm_small(int ta, int tb, int m, int n, int k, double alpha,
+                                                    const double* __restrict__ A, int lda, int64_t sA,
+                                                    const double* __restrict__ B, int ldb, int64_t sB, double* __restrict__ C,
+                                                    int ldc, int64_t sC) {
+    const int b = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const double* Ab = A + (size_t)b * sA;
+    const double* Bb = B + (size_t)b * sB;
+    double* Cb = C + (size_t)b * sC;
+    const int mt = (m + 7) >> 3, nt = (n + 7) >> 3, nk = (k + 3) >> 2;
+    for (int tile = wid; tile < mt * nt; tile += 4) {
+        const int ti = tile / nt, tj = tile - ti * nt;
+        const int i = 8 * ti + g, j = 8 * tj + g;
+        double c0 = 0.0, c1 = 0.0;
+        for (int ks = 0; ks < nk; ++ks) {
+            const int kk = 4 * ks + q;
+            const bool kv = kk < k;
+            const double a = (kv && i < m) ? (ta ? Ab[(size_t)kk * lda + i] : Ab[(size_t)i * lda + kk]) : 0.0;
+            const double bb = (kv && j < n) ? (tb ? Bb[(size_t)j * ldb + kk] : Bb[(size_t)kk * ldb + j]) : 0.0;
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c0), "+d"(c1) : "d"(a), "d"(bb));
+        }
+        const int jo = 8 * tj + 2 * q;
+        if (i < m && jo < n) Cb[(size_t)i * ldc + jo] = alpha * c0;
+        if (i < m && jo + 1 < n) Cb[(size_t)i * ldc + jo + 1] = alpha * c1;
+    }
+}
+
 extern "C" int lvae_gemm_batched_f64(int32_t trans_a, int32_t trans_b, int32_t m, int32_t n, int32_t k, double alpha,
                                      const double* A, int32_t lda, int64_t stride_a, const double* B, int32_t ldb,
                                      int64_t stride_b, double beta, double* C, int32_t ldc, int64_t stride_c,
@@ -194,6 +225,13 @@ extern "C" int lvae_gemm_batched_f64(int32_t trans_a, int32_t trans_b, int32_t m
     if (m < 0 || n < 0 || k < 0 || batch < 0 || !A || !B || !C) return LVAE_E_BADARG;
     if ((flags & LVAE_GEMM_MIRROR) && beta != 0.0) return LVAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (batch >= 256 && beta == 0.0 && flags == 0 && m <= 256 && n <= 256 && k <= 256 &&
+        (int64_t)m * n * k <= (int64_t)48 * 256 * 64) {         // many tiny products: one CTA per matrix
+        if (batch == 0 || m == 0 || n == 0) return 0;
+        k_gemm_small<<<batch, 128, 0, st>>>(trans_a, trans_b, m, n, k, alpha, A, lda, stride_a, B, ldb, stride_b, C, ldc, stride_c);
+        LVAE_COUNT_LAUNCH();
+        return lvae_cuda_rc(cudaGetLastError());
+    }
     GemmDesc d;
     d.A = A; d.B = B; d.C = C;
     d.m = m; d.n = n; d.k = k; d.lda = lda; d.ldb = ldb; d.ldc = ldc;

@@ -44,18 +44,14 @@ class KernelBlocks(torch.autograd.Function):
         return None, None, None, None, None, d_ls, d_os, d_diag
 
 
-def _own_gemm(batch):
-    """The DMMA GEMM for the per-latent matrices; stacks of thousands of tiny per-subject blocks (T x T, T <= 40, one per
-    subject and latent) are not worth a 128 x 64 tile each and go to cuBLAS (torch.bmm)."""
-    return batch <= 1024
-
-
 def _mm(A, B, ta=False, tb=False, flags=0):
+    """Every product goes to lvae_gemm_batched_f64: the tiled DMMA GEMM for the per-latent matrices, its one-CTA-per-matrix
+    kernel for the stacks of thousands of tiny per-subject blocks (T x T, T <= 40, one per subject and latent)."""
     m, k = (A.shape[2], A.shape[1]) if ta else (A.shape[1], A.shape[2])
     n = B.shape[1] if tb else B.shape[2]
-    if _own_gemm(A.shape[0]) and min(m, n, k) > 0:
+    if min(m, n, k) > 0 and A.shape[0] > 0:
         return ops.gemm_batched(A, B, trans_a=ta, trans_b=tb, flags=flags)
-    return torch.bmm(A.transpose(1, 2) if ta else A, B.transpose(1, 2) if tb else B)
+    return torch.zeros(A.shape[0], m, n, dtype=A.dtype, device=A.device)
 
 
 class Gemm(torch.autograd.Function):

@@ -93,7 +93,7 @@ class VaryingLengthBatchSampler(BatchSampler):
 # GP posterior-mean prediction (utils.py:115-345), SURVEY 8f-2.  Same call signatures as the reference; forward only.
 # Kernel matrices come from lvae_kernel_dense_f64 / lvae_kernel_blocks_f64, the per-subject and M x M factorisations and
 # explicit inverses from lvae_potrf_batched_f64 / lvae_potri_batched_f64, S = K0zx B^-1 K0xz from the batched DMMA GEMM;
-# the remaining matrix-vector products are torch.matmul on the device.  No CPU fallback.
+# every product, matrix-vector ones included, is lvae_gemm_batched_f64 (no cuBLAS on this path).  No CPU fallback.
 # ---------------------------------------------------------------------------------------------------------------
 def _spd_inverse(A):
     from . import ops
@@ -140,24 +140,25 @@ def _predict_one(L, covar_module0, covar_module1, likelihoods, x, test_x, mu, z,
         B = blocks[:, bidx].reshape(L * n, T, T)
         iB = _spd_inverse(B)                                                       # [L*n,T,T]
         Kx = K0xz[:, ridx].reshape(L * n, T, M)
-        iB_K0xz[:, ridx] = torch.bmm(iB, Kx).reshape(L, n * T, M)
-        iB_mu[:, ridx] = torch.bmm(iB, muL[:, ridx].reshape(L * n, T, 1)).reshape(L, n * T)
+        iB_K0xz[:, ridx] = ops.gemm_batched(iB, Kx).reshape(L, n * T, M)
+        iB_mu[:, ridx] = ops.gemm_batched(iB, muL[:, ridx].reshape(L * n, T, 1)).reshape(L, n * T)
         groups.append((ridx, iB, n, T))
     H = K0zz + ops.gemm_batched(K0xz, iB_K0xz, trans_a=True)                       # K0zz + K0zx B^-1 K0xz
     H = 0.5 * (H + H.transpose(1, 2))
-    rhs = torch.bmm(K0xz.transpose(1, 2), iB_mu.unsqueeze(2))                      # [L,M,1]
-    t1 = torch.bmm(K0xz, torch.bmm(_spd_inverse(H), rhs)).squeeze(2)               # K0xz H^-1 K0zx B^-1 mu   [L,N]
+    rhs = ops.gemm_batched(K0xz, iB_mu.unsqueeze(2), trans_a=True)                 # [L,M,1]
+    t1 = ops.gemm_batched(K0xz, ops.gemm_batched(_spd_inverse(H), rhs)).squeeze(2)   # K0xz H^-1 K0zx B^-1 mu   [L,N]
     mu_tilde = iB_mu.clone()
     for ridx, iB, n, T in groups:
-        mu_tilde[:, ridx] -= torch.bmm(iB, t1[:, ridx].reshape(L * n, T, 1)).reshape(L, n * T)
-    pred0 = torch.bmm(K0Xz, torch.bmm(_spd_inverse(K0zz), torch.bmm(K0xz.transpose(1, 2), mu_tilde.unsqueeze(2))))
+        mu_tilde[:, ridx] -= ops.gemm_batched(iB, t1[:, ridx].reshape(L * n, T, 1)).reshape(L, n * T)
+    pred0 = ops.gemm_batched(K0Xz, ops.gemm_batched(_spd_inverse(K0zz),
+                                                    ops.gemm_batched(K0xz, mu_tilde.unsqueeze(2), trans_a=True)))
     # id-dependent part: K1(X*, X[mask]) mu_tilde[mask] over the subjects that occur in the test set (utils.py:187-206)
     test_subjects = torch.unique(test_x[:, id_covariate])
     mask = torch.isin(x[:, id_covariate], test_subjects)
     pred1 = torch.zeros_like(pred0)
     if bool(mask.any()):
         K1Xx = ops.kernel_dense(st, ls, os_, test_x, x[mask].contiguous(), "k1")   # [L,N*,Nmask]
-        pred1 = torch.bmm(K1Xx, mu_tilde[:, mask].unsqueeze(2))
+        pred1 = ops.gemm_batched(K1Xx, mu_tilde[:, mask].unsqueeze(2).contiguous())
     return (pred0 + pred1).squeeze(2).t().contiguous()
 
 

@@ -1,11 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 10 --warmup 3 --no-others --no-cpu-baseline --no-latency-point > gpurun_out/r02_bench_j.json 2> gpurun_out/r02_bench_j.err; echo "cfg2 rc=$?"; tail -2 gpurun_out/r02_bench_j.err
-timeout 600 python bench.py --cfg cfg4 --steps 10 --warmup 3 --no-others --no-cpu-baseline --no-latency-point --no-parity > gpurun_out/r02_b_cfg4_split.json 2> gpurun_out/r02_b_cfg4_split.err; echo "cfg4 split rc=$?"
-timeout 600 python bench.py --cfg cfg4 --steps 10 --warmup 3 --no-others --no-cpu-baseline --no-latency-point --no-parity --no-split > gpurun_out/r02_b_cfg4_nosplit.json 2> gpurun_out/r02_b_cfg4_nosplit.err; echo "cfg4 nosplit rc=$?"; tail -2 gpurun_out/r02_b_cfg4_nosplit.err
-python - <<'PY'
-import json
-for f in ("r02_bench_j", "r02_b_cfg4_split", "r02_b_cfg4_nosplit"):
-    d = json.load(open(f"gpurun_out/{f}.json"))
-    print(f, round(d["value"]), round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "plain", round(d["e2e"]["plain_loop_value"]), {k: round(v, 3) for k, v in d["roofline"]["phase_ms"].items()})
-PY
+timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py > gpurun_out/r02_pytest_gpu.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu.log
+timeout 600 python tools/widening_bench.py > gpurun_out/r02_widening_bench.json 2> gpurun_out/r02_widening.err; tail -3 gpurun_out/r02_widening.err; cat gpurun_out/r02_widening_bench.json | head -c 1500
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_dubo.csv python tools/dubo_once.py > gpurun_out/r02_dubo_once.log 2>&1; python tools/launch_list_summary.py gpurun_out/r02_launches_dubo.csv > gpurun_out/r02_launches_dubo_summary.txt 2>&1; head -30 gpurun_out/r02_launches_dubo_summary.txt
