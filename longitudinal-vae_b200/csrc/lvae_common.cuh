@@ -78,25 +78,6 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
     return x < -700.0 ? 0.0 : res;
 }
 
-// Same value for x >= -700; arguments below are clamped to -700 (result ~1e-304 instead of an exact 0) — one FP64 max instead
-// of a compare and two selects in the hot loops of the fused subject kernel.
-__device__ __forceinline__ double exp_neg_clamped(double x, const double* __restrict__ tbl) {
-    const double MAGIC = 6755399441055744.0;
-    x = fmax(x, -700.0);
-    const double t = fma(x, 92.33248261689366, MAGIC);
-    const int k = __double2loint(t);
-    const double kd = t - MAGIC;
-    double r = fma(kd, -0.010830424493178725, x);
-    r = fma(kd, -2.030704202170295e-10, r);
-    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-    q = fma(q, r, 1.6666666666666666e-01);
-    q = fma(q, r, 0.5);
-    q = fma(q, r, 1.0);
-    const double tj = tbl[k & (LVAE_EXP_TBL - 1)];
-    const double v = fma(tj, q * r, tj);
-    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
-}
-
 // mask product of component c between covariate rows xa, xb (exact 0/1 arithmetic on float equality, as the reference)
 __device__ __forceinline__ double comp_mask(const DevSpec& s, int c, const double* __restrict__ xa,
                                             const double* __restrict__ xb) {

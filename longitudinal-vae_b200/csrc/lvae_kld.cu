@@ -72,6 +72,14 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
         const int cap = p->N_b / 512 > 0 ? p->N_b / 512 : 1;
         if (ns > cap) ns = cap;
         if (ns > 16) ns = 16;
+        // ... and for ACCURACY at most ~1024 rows per split: a GEMM accumulator is one sequential chain over its k range, and
+        // the rounding error of such a chain grows linearly with its length.  Kzz^-1 S Kzz^-1 magnifies the last bits of S by
+        // ~1e10 (cond(Kzz) ~ 1e8): with one 20 000-row chain grad_m was 1.7e-4 from the exact value at cfg3, 50 x the
+        // reference's own LAPACK error (measured against an extended-precision evaluation).  The partial S of
+        // the splits are then summed in fixed order: a two-level sum.
+        int ns_acc = (p->N_b + 1023) / 1024;
+        if (ns_acc > 64) ns_acc = 64;
+        if (ns < ns_acc) ns = ns_acc;
         w.nsplit = ns < 1 ? 1 : ns;
     }
     w.TP = (p->T_max + 3) & ~3;
@@ -88,6 +96,8 @@ KldLayout lvae_layout(const lvae_kld_problem_t* p) {
     o += o & 1;
     w.gcount = o; o += w.v2 ? (w.nchunk + 1) / 2 : 0;
     w.part = o; o += (int64_t)(w.big ? w.nsplit : w.nchunk) * L * w.stride;   // subject partials (S, ng1, da, A, hyp)
+    o += o & 1;                                                               // 16-byte aligned (double2 accesses)
+    w.acc2 = o; o += w.v3 ? (int64_t)w.nchunk * L * LVAE_F3_ACC2 : 0;         // second-level S accumulators of the fused pass
     w.ppart = o; o += (int64_t)w.nprep * L * (LVAE_NSCAL + w.nh);   // prep partials (scalars, hyp)
     w.bpstride = 2 * (int64_t)w.MP + LVAE_NSCAL + w.nh;
     if (w.big) {

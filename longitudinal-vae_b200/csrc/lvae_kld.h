@@ -4,6 +4,7 @@
 
 #define LVAE_F2_ROWS 24
 #define LVAE_F2_GT 8
+#define LVAE_F3_ACC2 (5 * 256 * 2)      // doubles per CTA of the fused pass: 5 S tiles x 256 threads x 2 accumulators
 
 struct KldLayout {
     int64_t Ki, Hi, G, W, T1, T2, T3;   // [L, M*M] each
@@ -14,6 +15,7 @@ struct KldLayout {
     int64_t off2;                       // int64 [P_b+1] prefix of T_p^2
     int64_t part;                       // [nchunk, L, stride] per-CTA partial statistics of the subject pass
     int64_t ppart;                      // [nchunk, L, NSCAL+nh] per-CTA partials of the prep pass
+    int64_t acc2;                       // [nchunk, L, LVAE_F3_ACC2] second-level accumulators of S (fused pass, two-level sum)
     int64_t total;
     int64_t stride;                     // statistics row length
     // second-generation fused pass (lvae_subjects_fused2.cu)

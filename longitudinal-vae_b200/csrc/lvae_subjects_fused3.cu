@@ -168,10 +168,25 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
     const double* Lrows = ws + w.Lrows + (size_t)l * N_b * TP;      // rows of the per-subject L^-1 (lower triangular)
     const double* Ltrows = ws + w.Ltrows + (size_t)l * N_b * TP;    // rows of the per-subject L^-T (upper triangular)
 
-    // S tiles of this warp: (wid, (wid + d) & 7), d = 0 .. 3, and d = 4 for wid < 4 — every unordered tile pair exactly once
+    // S tiles of this warp: (wid, (wid + d) & 7), d = 0 .. 3, and d = 4 for wid < 4 — every unordered tile pair exactly once.
+    // TWO-LEVEL sum: the register accumulators are flushed into CTA-private second-level accumulators (global memory, L2
+    // resident) every FLUSH groups.  One register chain over the ~110 groups of a CTA loses ~110 eps / 2 relative accuracy in
+    // S, and Kzz^-1 S Kzz^-1 magnifies the last bits of S by ~1e10 (cond(Kzz) ~ 1e8): measured on a host restatement,
+    // grad_m is 2.7e-6 from the exact value with chains of 112 subjects, 6.4e-7 with this two-level sum, 3e-5 with one chain of
+    // 1000.
+    constexpr int FLUSH = 16;
     double sacc[5][2];
 #pragma unroll
     for (int d = 0; d < 5; ++d) sacc[d][0] = sacc[d][1] = 0.0;
+    // (the pointer is re-formed at every use: it is needed once per FLUSH groups and must not hold two registers in between)
+    auto acc2_ptr = [&]() {
+        return reinterpret_cast<double2*>(ws + w.acc2 + ((size_t)blockIdx.x * L + blockIdx.y) * LVAE_F3_ACC2) + threadIdx.x;
+    };
+    {
+        double2* acc2 = acc2_ptr();
+#pragma unroll
+        for (int d = 0; d < 5; ++d) acc2[d * NTHR] = make_double2(0.0, 0.0);
+    }
     double gos[NC0], gls[NC0], g1os[NC1], g1ls[NC1], gno = 0.0;
 #pragma unroll
     for (int cc = 0; cc < NC0; ++cc) gos[cc] = gls[cc] = 0.0;
@@ -310,7 +325,7 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
                             if (rbf) {
                                 const double2 a = xc2[((cc * CS) * RG + t0) >> 1];
                                 const double d0 = a.x - zr, d1 = a.y - zr;
-                                const double e0 = exp_neg_clamped((d0 * d0) * nh_, etab), e1 = exp_neg_clamped((d1 * d1) * nh_, etab);
+                                const double e0 = exp_neg((d0 * d0) * nh_, etab), e1 = exp_neg((d1 * d1) * nh_, etab);
                                 f0 = on0 ? e0 : 0.0;
                                 f1 = on1 ? e1 : 0.0;
                                 fc[tt * NTHR] = make_double2(f0, f1);
@@ -550,7 +565,7 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
                                 if (sp.rbf_dim[cc] >= 0) {
                                     const double dd = xc[(cc * CS) * RG + t] - xc[(cc * CS) * RG + t2];
                                     const double d2 = dd * dd;
-                                    f = on ? exp_neg_clamped(-d2 * hil2[sp.ls_idx[cc]], etab) : 0.0;
+                                    f = on ? exp_neg(-d2 * hil2[sp.ls_idx[cc]], etab) : 0.0;
                                     g1ls[k] += gB * f * d2;
                                 }
                                 g1os[k] += gB * f;
@@ -562,6 +577,21 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
         };
         if (mt_[2] == 1 && R > 8 * (NT - 1)) body(std::true_type{});
         else body(std::false_type{});
+        if ((gi % FLUSH) == FLUSH - 1) {             // second level of the sum of S (each thread its own slots: no sync needed)
+            double2* acc2 = acc2_ptr();
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                double2 v = acc2[d * NTHR];
+                v.x += sacc[d][0]; v.y += sacc[d][1];
+                acc2[d * NTHR] = v;
+                sacc[d][0] = sacc[d][1] = 0.0;
+            }
+        }
+    }
+    {
+        const double2* acc2 = acc2_ptr();
+#pragma unroll
+        for (int d = 0; d < 5; ++d) { const double2 v = acc2[d * NTHR]; sacc[d][0] += v.x; sacc[d][1] += v.y; }
     }
 
     // ---- CTA epilogue: per-thread accumulators -> the partial statistics row of this CTA ------------------------------

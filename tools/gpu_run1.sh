@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_fullsize.py > gpurun_out/r02_pytest_gpu.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu.log
-timeout 600 python tools/widening_bench.py > gpurun_out/r02_widening_bench.json 2> gpurun_out/r02_widening.err; tail -3 gpurun_out/r02_widening.err; cat gpurun_out/r02_widening_bench.json | head -c 1500
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_dubo.csv python tools/dubo_once.py > gpurun_out/r02_dubo_once.log 2>&1; python tools/launch_list_summary.py gpurun_out/r02_launches_dubo.csv > gpurun_out/r02_launches_dubo_summary.txt 2>&1; head -30 gpurun_out/r02_launches_dubo_summary.txt
+timeout 600 python bench.py --steps 20 --warmup 5 --no-others --no-parity --no-cpu-baseline --no-latency-point > gpurun_out/r02_bench_l.json 2> gpurun_out/r02_bench_l.err; echo "rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_l.json')); print(round(d['value']), round(d['ms_per_step'],3), {k: round(v,4) for k,v in d['roofline']['phase_ms'].items()})"
