@@ -547,7 +547,7 @@ int lvae_prep3_rows(const lvae_kld_problem_t* p) {
         ns += (p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE] >= 0) + p->ks.spec[(size_t)c_ * LVAE_SPEC_STRIDE + 2];
     const int T = p->T_max;
     const int nw = T <= 24 ? 1 : 4;
-    const int gpc = T <= 24 ? groups_per_cta3<3, 28, 1>(ns) : groups_per_cta3<5, 44, 4>(ns);
+    const int gpc = T <= 24 ? groups_per_cta3<3, 24, 1>(ns) : groups_per_cta3<5, 44, 4>(ns);
     const int pw = gpc * nw, per_sm = nw == 1 ? 2 : 1;
     int ctas = per_sm * 148 / p->L;
     if (ctas < 1) ctas = 1;
@@ -562,6 +562,6 @@ int lvae_prep3_launch(const lvae_kld_problem_t* p, const DevSpec& sp, const KldL
     // <3, 20, 1> instantiation (20 x 20 scratch for T <= 20) let the 8-wide tiles run past column 19 into the next row and past
     // row 19 into the next matrix: correct on zero-initialised scratch, i.e. for the FIRST task of a warp only — the full-size
     // parity check of round 2 caught the later tasks (rows 0..3 of d_log_v, L^-1) being wrong.
-    if (T <= 24) return launch3<3, 28, 1, true>(p, sp, w, st);
+    if (T <= 24) return launch3<3, 24, 1, true>(p, sp, w, st);
     return launch3<5, 44, 4, false>(p, sp, w, st);
 }
