@@ -67,12 +67,14 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
     const double kd = t - MAGIC;
     double r = fma(kd, -0.010830424493178725, x);                  // ln2/64, high part (27 trailing zero bits)
     r = fma(kd, -2.030704202170295e-10, r);                        // ln2/64, low part
-    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-    q = fma(q, r, 1.6666666666666666e-01);
-    q = fma(q, r, 0.5);
-    q = fma(q, r, 1.0);
+    // exp(r) - 1 = r + r^2 ((1/2 + r/6) + r^2 (1/24 + r/120)), evaluated Estrin-style: dependency depth 4 instead of Horner's 6
+    // (the kernels that call this run 4 warps per scheduler and are bound by exactly such dependency chains)
+    const double r2 = r * r;
+    const double hi_ = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    const double lo_ = fma(r, 1.6666666666666666e-01, 0.5);
+    const double p = fma(fma(hi_, r2, lo_), r2, r);
     const double tj = tbl[k & (LVAE_EXP_TBL - 1)];
-    const double v = fma(tj, q * r, tj);
+    const double v = fma(tj, p, tj);
     const int hi = __double2hiint(v) + ((k >> 6) << 20);
     const double res = __hiloint2double(hi, __double2loint(v));
     return x < -700.0 ? 0.0 : res;

@@ -536,11 +536,16 @@ k_subjects_fused3(const __grid_constant__ DevSpec sp, const __grid_constant__ Kl
                 int jt, i;
                 tri2(tile, jt, i);                   // i <= jt
                 if (FULL || (jt < nmt && 8 * jt < hi_[min(8 * i + 7, R - 1)])) {
-                    double q0 = 0.0, q1 = 0.0;
+                    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;       // two accumulator chains: half the dependency depth
                     const double* Ya = YTs + q * LDC + 8 * i + g;
                     const double* Vb = VTs + q * LDC + 8 * jt + g;
-#pragma unroll 5
-                    for (int ks = 0; ks < nks; ++ks) dmma(q0, q1, Ya[4 * ks * LDC], Vb[4 * ks * LDC]);
+#pragma unroll 4
+                    for (int ks = 0; ks + 1 < nks; ks += 2) {
+                        dmma(q0, q1, Ya[4 * ks * LDC], Vb[4 * ks * LDC]);
+                        dmma(q2, q3, Ya[4 * (ks + 1) * LDC], Vb[4 * (ks + 1) * LDC]);
+                    }
+                    if (nks & 1) dmma(q0, q1, Ya[4 * (nks - 1) * LDC], Vb[4 * (nks - 1) * LDC]);
+                    q0 += q2; q1 += q3;
                     const int t = 8 * i + g;
                     const double wgt = jt > i ? 2.0 : 1.0;
                     const double ut = us[t];

@@ -2,8 +2,10 @@
 import json, sys
 d = json.load(open(sys.argv[1]))
 def show(name, p):
-    print(name, "ok", p["ok"], "lat", p["latents_checked"])
-    for k in p["per_tensor_rank0"]:
+    print(name, "ok", p["ok"], "lat", p.get("latents_checked"))
+    if "per_tensor_rank0" not in p:
+        print("   gross (max over ranks)", {k: "%.1e" % v for k, v in p["all_latents_vs_torch_cuda_oracle"]["per_tensor_max_over_ranks"].items()})
+    for k in p.get("per_tensor_rank0", {}):
         ve = p["vs_exact_rank0"]
         vd = ve.get("reference_torch_cuda", {})
         print("   %-8s err %.2e | exact: ours %s host %s cuda %s | floor %.2e allow %.2e | gross %.2e | %s" % (
