@@ -28,6 +28,7 @@ struct GemmDesc {
     int64_t kA = 0, kB = 0, kC = 0;
     double alpha = 1.0, beta = 0.0;
     int flags = 0;
+    int flush = 0;              // > 0 (beta == 0 only): two-level sum, accumulators folded into C every `flush` k-tiles of 16
 };
 int lvae_gemm(const GemmDesc& d, cudaStream_t st);
 

@@ -121,10 +121,33 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const __grid_constant__ GemmDes
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
+        // Two-level sum over a long k range (d.flush > 0, beta == 0): every `flush` k-tiles the accumulators are added to
+        // this thread's own elements of C (L2-resident, no other thread touches them) and restart from zero, so no rounding
+        // chain is longer than 4 * flush DMMA steps + (k-tiles / flush) additions.
+        if (d.flush > 0 && kt + 1 < nkt && (kt + 1) % d.flush == 0) {
+            const bool first = kt + 1 == d.flush;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const int i = row0 + wm * 32 + mt * 8 + g;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int j = col0 + wn * 32 + nt * 8 + 2 * q;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (i < d.m && j + e < d.n && !((d.flags & LVAE_GEMM_LOWER) && j + e > i)) {
+                            double* c = C + (size_t)i * d.ldc + j + e;
+                            *c = first ? acc[mt][nt][e] : *c + acc[mt][nt][e];
+                        }
+                        acc[mt][nt][e] = 0.0;
+                    }
+                }
+            }
+        }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 
     const bool lower = d.flags & LVAE_GEMM_LOWER, mirror = d.flags & LVAE_GEMM_MIRROR;
+    const bool flushed = d.flush > 0 && nkt > d.flush;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         const int i = row0 + wm * 32 + mt * 8 + g;
@@ -135,7 +158,9 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const __grid_constant__ GemmDes
             for (int e = 0; e < 2; ++e) {
                 const int j = col0 + wn * 32 + nt * 8 + 2 * q + e;
                 if (j >= d.n || (lower && j > i)) continue;
-                double v = d.alpha * acc[mt][nt][e];
+                double v = acc[mt][nt][e];
+                if (flushed) v += C[(size_t)i * d.ldc + j];
+                v *= d.alpha;
                 if (d.beta != 0.0) v += d.beta * C[(size_t)i * d.ldc + j];
                 C[(size_t)i * d.ldc + j] = v;
                 if (mirror && j < i) C[(size_t)j * d.ldc + i] = v;
@@ -161,6 +186,7 @@ int lvae_gemm(const GemmDesc& din, cudaStream_t st) {
     GemmDesc d = din;
     if (d.m <= 0 || d.n <= 0 || d.batch <= 0 || d.batch2 <= 0) return 0;
     if (d.ksplit <= 1) { d.ksplit = 1; d.kchunk = d.k; }
+    if (d.beta != 0.0) d.flush = 0;               // the intermediate sums live in C itself
     if ((int64_t)d.batch * d.batch2 * d.ksplit > 65535) return LVAE_E_TOO_LARGE;
     const auto even = [](int64_t v) { return (v & 1) == 0; };
     const int al16 = ((reinterpret_cast<uintptr_t>(d.A) | reinterpret_cast<uintptr_t>(d.B)) & 15) == 0 && even(d.lda) &&

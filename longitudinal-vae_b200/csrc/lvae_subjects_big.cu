@@ -183,7 +183,7 @@ __device__ __forceinline__ double eval_rows(const CompTab& ct, int c, const doub
 
 __host__ __device__ inline size_t uv_doubles(int MP, int Q) {
     (void)Q;
-    return (size_t)RG * (MP + 4) + (size_t)RG * LDL + (size_t)4 * CS * MP + (size_t)4 * CS * RG + MP + 4 * RG + 16 * RG + 2 * RG / 2 + GT;
+    return (size_t)RG * (MP + 4) + (size_t)RG * LDL + (size_t)4 * CS * MP + (size_t)4 * CS * RG + MP + 4 * RG + 16 * RG + 2 * MP + 2 * RG / 2 + GT;
 }
 
 template <int NTW>
@@ -207,7 +207,8 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
     double* const us = rs + RG;
     double* const rpart = us + RG;              // [8][RG]
     double* const upart = rpart + 8 * RG;       // [8][RG]
-    int* const blo = reinterpret_cast<int*>(upart + 8 * RG);   // [RG]
+    double* const lvl2 = upart + 8 * RG;        // [2][MP] second-level sums of ng1, da
+    int* const blo = reinterpret_cast<int*>(lvl2 + 2 * MP);    // [RG]
     int* const bhi = blo + RG;
     int* const meta = bhi + RG;                 // [GT]
 
@@ -224,11 +225,28 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
     double* const ug = ws + w.bu + (size_t)l * N_b;
     const int colw = 8 * NTW * wl;              // first column of this warp
 
+    // two-level sums (a chunk can hold thousands of rows; Kzz^-1 magnifies the last bits of ng1): the register accumulators
+    // cover 16 row groups, then they are folded into lvl2 (each warp owns its columns, lanes g == 0 write)
     double ng1acc[NTW][2], daacc[NTW][2], accA = 0.0;
 #pragma unroll
     for (int nt = 0; nt < NTW; ++nt) ng1acc[nt][0] = ng1acc[nt][1] = daacc[nt][0] = daacc[nt][1] = 0.0;
+    for (int e = tid; e < 2 * MP; e += 256) lvl2[e] = 0.0;
+    auto fold = [&]() {
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double a2 = ng1acc[nt][e], b2 = daacc[nt][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) { a2 += __shfl_xor_sync(0xffffffffu, a2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+                if (g == 0) { lvl2[colw + 8 * nt + 2 * q + e] += a2; lvl2[MP + colw + 8 * nt + 2 * q + e] += b2; }
+                ng1acc[nt][e] = daacc[nt][e] = 0.0;
+            }
+        }
+    };
 
     for (int gi = 0; gi < ngroups; ++gi) {
+        if ((gi & 15) == 0 && gi) fold();
         __syncthreads();
         if (tid < GT) meta[tid] = gtab[(size_t)gi * GT + tid];
         __syncthreads();
@@ -356,15 +374,17 @@ k_uv(const __grid_constant__ DevSpec sp, const __grid_constant__ KldLayout w, in
 
     // ---- CTA epilogue: fixed-order partials -------------------------------------------------------------------------------
     double* bp = ws + w.bpart + ((size_t)chunk * L + l) * w.bpstride;
+    __syncthreads();
+    fold();
+    __syncwarp();
+    if (g == 0) {
 #pragma unroll
-    for (int nt = 0; nt < NTW; ++nt) {
+        for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            double a2 = ng1acc[nt][e], b2 = daacc[nt][e];
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) { a2 += __shfl_xor_sync(0xffffffffu, a2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
-            if (g == 0) { bp[colw + 8 * nt + 2 * q + e] = a2; bp[MP + colw + 8 * nt + 2 * q + e] = b2; }
-        }
+            for (int e = 0; e < 2; ++e) {
+                const int j = colw + 8 * nt + 2 * q + e;
+                bp[j] = lvl2[j]; bp[MP + j] = lvl2[MP + j];
+            }
     }
     const double a_ = block_sum(accA, red);
     if (tid < LVAE_NSCAL) bp[2 * MP + tid] = (tid == SC_A) ? a_ : 0.0;
@@ -595,6 +615,7 @@ int lvae_subjects_big_launch(const lvae_kld_problem_t* p, const DevSpec& sp, con
     s.ksplit = w.nsplit; s.kchunk = kchunk;
     s.kA = (int64_t)kchunk * MP; s.kB = (int64_t)kchunk * MP; s.kC = (int64_t)L * w.stride;
     s.flags = LVAE_GEMM_LOWER | LVAE_GEMM_MIRROR;
+    s.flush = 16;                                 // rounding chains of S: 64 DMMA steps, then kchunk / 256 + nsplit additions
     rc = lvae_gemm(s, st);
     if (rc) return rc;
     GemmDesc y;                                   // Y = V W, written over U
