@@ -77,6 +77,7 @@ def parse():
     ap.add_argument("--no-others", action="store_true", help="skip cfg3 / cfg4 / cfg5 and the strong-scaling point")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--others-steps", type=int, default=5)
+    ap.add_argument("--profile-e2e", default=None, help="diagnostic: torch.profiler tables of three API steps -> PATH.<cfg>.txt")
     return ap.parse_args()
 
 
@@ -652,13 +653,32 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_ms, t_prev = [], time.perf_counter()
+    allocs0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
     for _ in range(steps):
         e2e_step(n_e2e); n_e2e += 1
+        t_now = time.perf_counter(); host_ms.append(round((t_now - t_prev) * 1e3, 3)); t_prev = t_now
     main.wait_event(out_done)                              # the last step's results have reached host memory
     e1.record()
     barrier()
+    e2e_diag = {"host_enqueue_ms_per_step_rank0": host_ms[:32],
+                "cudaMalloc_calls_in_timed_region_rank0": torch.cuda.memory_stats(device).get("num_device_alloc", 0) - allocs0}
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     e2e_val = P_glob / (e2e_ms * 1e-3)
+    if args.profile_e2e and rank == 0:                     # diagnostic: where the API step spends its time (not a bench value)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                e2e_step(n_e2e); n_e2e += 1
+            torch.cuda.synchronize(device)
+        with open(f"{args.profile_e2e}.{cfg}{'_strong' if strong else ''}.txt", "w") as fh:
+            fh.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+            fh.write("\n")
+            fh.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=70))
+    elif args.profile_e2e:
+        for _ in range(3):
+            e2e_step(n_e2e); n_e2e += 1
+        torch.cuda.synchronize(device)
     h2d = (hx.numel() + hmu.numel() + hlv.numel()) * 8
     d2h = (out_mu.numel() + out_lv.numel() + 1) * 8
     EF.check_errors()
@@ -707,7 +727,7 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
     res.out = {
         "value": value, "ms_per_step": ms_per_step, "subjects_per_gpu": P_b, "global_batch_subjects": P_glob,
         "scaling": "strong" if strong else "weak", "tail": tail_mode,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "diag": e2e_diag,
                 "plain_loop_value": P_glob / (plain_ms * 1e-3), "plain_loop_ms_per_step": plain_ms,
                 "how": "public API (minibatch_KLD_upper_bound[_iter] + backward + natural_gradient_step); every step copies "
                        "x, mu, log_v from pinned host memory and returns kld, d_mu, d_log_v to pinned host memory.  `value`: "
@@ -1166,7 +1186,7 @@ def main():
                 others[name] = {"config": workload_config(kw["cfg"], kw["spb"], world, r.b, kw.get("strong", False)),
                                 "value": oo["value"], "unit": UNIT, "ms_per_step": oo["ms_per_step"],
                                 "scaling": oo["scaling"], "steps": args.others_steps, "warmup": 3,
-                                "e2e": {k: oo["e2e"][k] for k in ("value", "ms_per_step", "plain_loop_value",
+                                "e2e": {k: oo["e2e"][k] for k in ("value", "ms_per_step", "diag", "plain_loop_value",
                                                                    "h2d_bytes_per_step", "d2h_bytes_per_step")},
                                 "roofline_frac": oo["roofline_frac"], "subject_pass_tflops": oo["subject_pass_tflops"],
                                 "step_tflops": oo["step_tflops"], "phase_ms": oo["phase_ms"], "parity": oo["parity"],

@@ -8,6 +8,9 @@ sharded across GPUs, and one tail kernel.  `kld_total` is an autograd node w.r.t
 hyper-parameter, the likelihood noise and (natural_gradient=False) m and H; its gradients are produced by the same
 launches (closed-form adjoints) and scaled by the incoming gradient in backward.
 """
+import collections
+import sys
+
 import numpy as np
 import torch
 
@@ -65,6 +68,39 @@ def set_error_check(mode):
     _CHECK = mode
 
 
+_POOL = collections.OrderedDict()     # call signature -> prepared calls (ops.KldCall / SplitKldCall / LatentTailKldCall)
+_POOL_SIGNATURES, _POOL_DEPTH = 8, 4
+
+
+def _pooled_call(key, make):
+    """A prepared call for this problem signature, reused across training steps: building one allocates the workspace (GBs
+    at M = 256) and a dozen output buffers, and with several live at once (deferred error checks, autograd graphs) the
+    caching allocator kept going back to cudaMalloc — 16 .. 63 cudaMalloc calls inside five timed steps on two GPUs, where
+    every cudaMalloc also has to map the block into the peers.  A call is free when NOTHING refers to it any more (the
+    autograd node of its forward, the deferred-check queue, the H^-1 / latent-tail tags on grad_H): plain reference
+    counting, so a caller that keeps two graphs alive simply gets two calls.  Work is stream-ordered: the stream is part of
+    the key."""
+    calls = _POOL.get(key)
+    if calls is None:
+        calls = _POOL[key] = []
+        while len(_POOL) > _POOL_SIGNATURES:          # ragged minibatches: every new shape is a new signature
+            _POOL.popitem(last=False)
+    else:
+        _POOL.move_to_end(key)
+    for c in calls:
+        if sys.getrefcount(c) <= 3:                   # the pool's list, this loop variable, getrefcount's argument
+            return c
+    c = make()
+    if len(calls) < _POOL_DEPTH:
+        calls.append(c)
+    return c
+
+
+def clear_call_pool():
+    """Drop the cached calls (their device memory returns to torch's allocator)."""
+    _POOL.clear()
+
+
 def check_errors():
     """Raise if any earlier deferred call hit a non-positive-definite block."""
     while _PENDING:
@@ -99,14 +135,23 @@ class _KldBound(torch.autograd.Function):
         lengthscale, outputscale, noise = hyper[:st.n_ls], hyper[st.n_ls:st.n_ls + st.n_comp], hyper[st.n_ls + st.n_comp]
         x, z, offsets = meta["x"], meta["z"], meta["offsets"]
         L, M, Q = meta["L"], H.shape[-1], x.shape[1]
-        if meta.get("counts") is not None:            # ragged minibatch: rows per subject known on the host
-            call = ops.make_kld_call(st, L, M, Q, meta["counts"], x.device, natural_gradient=meta["natural_gradient"],
-                                     path=_PATH)
-        else:
-            call = ops.KldCall(st, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"], meta["sum_T2"], x.device,
-                               natural_gradient=meta["natural_gradient"], path=_PATH)
-        if meta.get("group") is not None and meta.get("tail") == "latents" and isinstance(call, ops.KldCall):
-            call = ops.LatentTailKldCall(call, meta["group"])
+        counts = meta.get("counts")
+        latent_tail = meta.get("group") is not None and meta.get("tail") == "latents"
+
+        def make():
+            if counts is not None:                    # ragged minibatch: rows per subject known on the host
+                c = ops.make_kld_call(st, L, M, Q, counts, x.device, natural_gradient=meta["natural_gradient"], path=_PATH)
+            else:
+                c = ops.KldCall(st, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"], meta["sum_T2"], x.device,
+                                natural_gradient=meta["natural_gradient"], path=_PATH)
+            if latent_tail and isinstance(c, ops.KldCall):
+                c = ops.LatentTailKldCall(c, meta["group"])
+            return c
+        key = (st.table.tobytes(), st.n_comp0, st.n_comp1, st.n_ls, L, M, Q, offsets.numel() - 1, x.shape[0], meta["T_max"],
+               meta["sum_T2"], x.device, meta["natural_gradient"], _PATH, id(meta["group"]) if latent_tail else 0,
+               None if counts is None else np.asarray(counts, dtype=np.int64).tobytes(),
+               torch.cuda.current_stream(x.device).cuda_stream)
+        call = _pooled_call(key, make)
         call.bind(x, offsets, mu, log_v, z, m.reshape(L, M), H, lengthscale, outputscale, noise, meta["scale"],
                   meta["const_term"], meta["eps"])
         call.head()
@@ -123,11 +168,15 @@ class _KldBound(torch.autograd.Function):
         ctx.call = call
         ctx.ng = meta["natural_gradient"]
         ctx.mshape = m.shape
-        ctx.mark_non_differentiable(call.grad_m, call.grad_H)
-        # H^-1 of the head kernel rides along for natural_gradient_step (training.py:130-131 recomputes it)
-        meta["Hinv"] = (call.Hinv, H.data_ptr(), H._version)
+        # the call object (scratch + outputs) goes back to the pool once nothing refers to it: hand out copies of the two
+        # small results that outlive it
+        gm, gH = call.grad_m.view(L, M, 1).clone(), call.grad_H.clone()
+        ctx.mark_non_differentiable(gm, gH)
+        # H^-1 of the head kernel rides along for natural_gradient_step (training.py:130-131 recomputes it); the tag keeps
+        # the call (whose workspace holds it) out of the pool for as long as grad_H lives
+        meta["Hinv"] = (call.Hinv, H.data_ptr(), H._version, call)
         meta["latent_tail"] = call if isinstance(call, ops.LatentTailKldCall) else None
-        return kld, call.grad_m.view(L, M, 1), call.grad_H
+        return kld, gm, gH
 
     @staticmethod
     def backward(ctx, g, _gm, _gH):

@@ -203,7 +203,8 @@ class KldCall:
 
     def post_info(self):
         """Deferred check: copy the flags to pinned host memory on the current stream without blocking."""
-        self._info_host = torch.empty(4, dtype=torch.int32).pin_memory()
+        if getattr(self, "_info_host", None) is None:
+            self._info_host = torch.empty(4, dtype=torch.int32).pin_memory()
         self._info_host.copy_(self.info, non_blocking=True)
         self._info_event = torch.cuda.Event()
         self._info_event.record(torch.cuda.current_stream(self.device))
