@@ -350,3 +350,35 @@ def test_gp_model_modules_drive_the_iter_bound():
     got = torch.cat(got).cpu().numpy()
     ref = golden_hyper_vector(g)
     assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
+
+
+def test_prepared_calls_are_reused_without_aliasing_live_results():
+    """The prepared calls behind the API are pooled (elbo_functions._pooled_call).  A second forward while the first one's
+    graph and results are still alive must not touch them; once they are gone the same call object serves the next step."""
+    import lvae_b200.elbo_functions as EF
+    g = load_golden("cfg2_small")
+    L = g["mu"].shape[1]
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    cm0, cm1, lik = build_modules(g["lists"], L, g["lengthscale"], g["outputscale"], g["noise"])
+    P_b, T = len(g["offsets"]) - 1, int(g["T"])
+    args = lambda mu, H: (cm0, cm1, lik, L, t("m"), H, t("x"), mu, t("log_v"), t("z"), int(g["P_tot"]), P_b, T, True, 1e-6)
+    EF.clear_call_pool()
+    mu1 = t("mu").requires_grad_(True)
+    kld1, gm1, gH1 = EF.minibatch_KLD_upper_bound(*args(mu1, t("H")))
+    keep = (kld1.item(), gm1.clone(), gH1.clone())
+    mu2 = (t("mu") * 1.5).requires_grad_(True)                    # different inputs, same shapes, first graph still alive
+    kld2, gm2, gH2 = EF.minibatch_KLD_upper_bound(*args(mu2, 2.0 * t("H")))
+    assert kld2.item() != keep[0]
+    assert torch.equal(gm1, keep[1]) and torch.equal(gH1, keep[2])
+    kld1.sum().backward()                                         # reads the FIRST call's buffers
+    ref = torch.from_numpy(g["d_mu"]).cuda()
+    assert rel(mu1.grad, ref) < 1e-9
+    calls = [c for cs in EF._POOL.values() for c in cs]
+    assert len(calls) == 2
+    del kld1, gm1, gH1, kld2, gm2, gH2
+    mu3 = t("mu").requires_grad_(True)
+    kld3, gm3, gH3 = EF.minibatch_KLD_upper_bound(*args(mu3, t("H")))
+    assert [c for cs in EF._POOL.values() for c in cs] == calls   # nothing new was built
+    assert kld3.item() == keep[0] and torch.equal(gm3, keep[1]) and torch.equal(gH3, keep[2])
+    m2, H2 = __import__("lvae_b200.training", fromlist=["x"]).natural_gradient_step(t("m"), t("H"), gm3, gH3, 0.01)
+    assert torch.isfinite(m2).all() and torch.isfinite(H2).all()

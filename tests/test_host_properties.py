@@ -134,3 +134,36 @@ def test_block_indexing_rule_on_random_kernel_lists(cat, bin_, sq, cat_int, bin_
             if rbf:
                 assert row[1] == i_ls
                 i_ls += 1
+
+
+def test_call_pool_hands_out_only_unreferenced_calls():
+    """elbo_functions._pooled_call: a prepared call is reused only when nothing refers to it any more; live references
+    (an autograd node, the deferred-check queue, a tag on grad_H) get the next caller a different object; at most
+    _POOL_SIGNATURES problem shapes are remembered."""
+    import lvae_b200.elbo_functions as EF
+
+    class Call:
+        pass
+    EF.clear_call_pool()
+    built = []
+
+    def make():
+        built.append(1)                            # count only: a reference kept here would pin the call
+        return Call()
+    a = EF._pooled_call("k", make)
+    b = EF._pooled_call("k", make)                 # `a` still referenced here
+    assert a is not b and len(built) == 2
+    ida = id(a)
+    del a
+    c = EF._pooled_call("k", make)                 # the first one is free again
+    assert id(c) == ida and len(built) == 2
+    holder = [c]                                   # e.g. the deferred-check queue
+    del c
+    d = EF._pooled_call("k", make)
+    assert d is not holder[0] and d is not b and len(built) == 3
+    holder.clear()
+    for i in range(EF._POOL_SIGNATURES + 3):       # ragged minibatches: new shapes push old ones out
+        EF._pooled_call(("shape", i), make)
+    assert len(EF._POOL) == EF._POOL_SIGNATURES and "k" not in EF._POOL
+    EF.clear_call_pool()
+    assert not EF._POOL
