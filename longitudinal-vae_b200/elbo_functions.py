@@ -36,6 +36,7 @@ def set_process_group(group, exchange="nccl", shard="subjects", tail="replicated
     dimensions (no statistics exchange: the latent dimensions are independent); see distributed.enable."""
     global _GROUP, _EXCHANGE, _SHARD, _TAIL
     _GROUP, _EXCHANGE, _SHARD, _TAIL = group, exchange, shard, tail
+    _POOL.clear()            # prepared calls may be bound to the previous group (and hold GBs of scratch)
 
 
 def exchange_stats(call, group, exchange):
