@@ -420,6 +420,13 @@ class Ctx:
     pass
 
 
+def zero_grads(params):
+    """What optimiser.zero_grad(set_to_none=True) does (training.py:105 of the reference): the parameter list is collected
+    once, not by walking the module trees every step (Module.zero_grad: 0.26 ms per step for the three GP modules)."""
+    for p in params:
+        p.grad = None
+
+
 def build_modules(b, device):
     """Drop-in kernel modules + likelihood of this package with the problem's hyper-parameters."""
     from lvae_b200.constraints import GreaterThan
@@ -477,6 +484,7 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
     P_tot = P_glob                                # the data set is the (global) minibatch: P_tot / P_batch = 1
     N_tot = N_glob
     cm0, cm1, lik = build_modules(b, device)
+    gp_params = [p for mod in (cm0, cm1, lik) for p in mod.parameters()]
     st, ls, os_ = build_structure(flatten(cm0), flatten(cm1), L, device=device)
     ls, os_ = ls.detach(), os_.detach()
     noise = lik.noise.detach().reshape(L).contiguous()
@@ -641,7 +649,7 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
             for t_ in (gmu, glv, kd):
                 t_.record_stream(s_out)
             out_done.record(s_out)
-        cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
+        zero_grads(gp_params)
 
     for d in dbuf:
         d["free"].record(main)
@@ -697,7 +705,7 @@ def run_config(args, cfg, spb, rank, world, device, dist, peak, *, steps, warmup
         out_mu.copy_(mud.grad, non_blocking=True)
         out_lv.copy_(lvd.grad, non_blocking=True)
         out_kld.copy_(kld.detach().reshape(1), non_blocking=True)
-        cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
+        zero_grads(gp_params)
     for _ in range(3):
         plain_step()
     barrier()
@@ -989,6 +997,7 @@ def latency_point(args, R, device):
     lat = {"spb": spb2, "ms_per_step": a_.elapsed_time(b__) / 50, "subjects_per_s": spb2 / (a_.elapsed_time(b__) / 50 * 1e-3),
            "what": "spb = 20 (the reference's default minibatch), device-resident inputs, bound + gradients + NG update"}
     cm0, cm1, lik = R.cm0, R.cm1, R.lik
+    gp_params = [p for mod in (cm0, cm1, lik) for p in mod.parameters()]
     try:      # the same small minibatch through the public API with pinned host inputs (Python + launch overhead regime)
         hx2, hmu2, hlv2 = b.x[:rows].pin_memory(), b.mu[:rows].pin_memory(), b.log_v[:rows].pin_memory()
         st2 = {"m": R.m0.clone(), "H": R.H0.clone()}
@@ -1007,7 +1016,7 @@ def latency_point(args, R, device):
             kld.sum().backward()
             st2["m"], st2["H"] = natural_gradient_step(st2["m"], st2["H"], gm, gH, LR)
             o_mu.copy_(mud.grad, non_blocking=True)
-            cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
+            zero_grads(gp_params)
         EF.set_error_check("deferred")
         for _ in range(5):
             small_api()
@@ -1034,7 +1043,7 @@ def latency_point(args, R, device):
                 lvd = hlv2.to(device, non_blocking=True).requires_grad_(True)
                 gstep(xd, mud, lvd).backward()
                 o_mu.copy_(mud.grad, non_blocking=True)
-                cm0.zero_grad(set_to_none=True); cm1.zero_grad(set_to_none=True); lik.zero_grad(set_to_none=True)
+                zero_grads(gp_params)
             for _ in range(5):
                 small_graphed()
             torch.cuda.synchronize()
